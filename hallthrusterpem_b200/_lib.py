@@ -1,0 +1,124 @@
+"""ctypes binding of libhpem.so (the C ABI declared in include/hpem.h).
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded this module raises, and every
+model entry point raises with it.  `python __graft_entry__.py` (or `build_library()`) compiles it in-tree with
+`nvcc -gencode arch=compute_100a,code=sm_100a`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO_ROOT = PKG_DIR.parent
+CSRC = PKG_DIR / 'csrc'
+LIB_PATH = PKG_DIR / 'lib' / 'libhpem.so'
+HEADER = REPO_ROOT / 'include' / 'hpem.h'
+
+INPUT_NAMES = ('P_b', 'V_a', 'T_e', 'V_vac', 'Pstar', 'P_T',
+               'c0', 'c1', 'c2', 'c3', 'c4', 'c5', 'sigma_cex', 'I_B0', 'T')   # enum hpem_input order
+N_INPUTS = len(INPUT_NAMES)
+CATHODE_INPUTS = INPUT_NAMES[:6]
+PLUME_INPUTS = ('P_b',) + INPUT_NAMES[6:14]
+
+HPEM_OK = 0
+FLAG_FORCE_DIRECT = 1
+
+EXPORTED_SYMBOLS = (
+    'hpem_abi_version', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',
+    'hpem_eval', 'hpem_eval_host', 'hpem_launch_count',
+)
+
+
+class HpemInputs(ctypes.Structure):
+    _fields_ = [('ptr', ctypes.c_void_p * N_INPUTS), ('scalar', ctypes.c_double * N_INPUTS)]
+
+
+class HpemOutputs(ctypes.Structure):
+    _fields_ = [('V_cc', ctypes.c_void_p), ('j_ion', ctypes.c_void_p), ('div_angle', ctypes.c_void_p),
+                ('T_c', ctypes.c_void_p), ('cos_div', ctypes.c_void_p), ('invalid', ctypes.c_void_p)]
+
+
+class HpemMomentsSpec(ctypes.Structure):
+    _fields_ = [('n_bins', ctypes.c_int32), ('log10_lo', ctypes.c_double), ('log10_hi', ctypes.c_double)]
+
+
+class HpemError(RuntimeError):
+    """Raised for a non-zero status from the C ABI (API misuse or a CUDA error)."""
+
+
+class LibraryMissing(ImportError):
+    pass
+
+
+def nvcc_command(out: Path = LIB_PATH) -> list[str]:
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    return [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+            '-Xcompiler', '-fPIC', '-shared', '-o', str(out), str(CSRC / 'hpem_api.cu')]
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    """Compile csrc/*.cu into lib/libhpem.so for sm_100a (cross-compiles without a GPU)."""
+    sources = list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) + list(CSRC.glob('*.inc')) + [HEADER]
+    if LIB_PATH.exists() and not force:
+        newest = max(p.stat().st_mtime for p in sources)
+        if LIB_PATH.stat().st_mtime >= newest:
+            return LIB_PATH
+    LIB_PATH.parent.mkdir(parents=True, exist_ok=True)
+    cmd = nvcc_command()
+    if verbose:
+        cmd.insert(1, '-Xptxas=-v')
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libhpem.so once; raise LibraryMissing if it is not built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = Path(os.environ.get('HPEM_LIBRARY', LIB_PATH))
+        if not path.exists():
+            raise LibraryMissing(f'{path} not found: build it with `python __graft_entry__.py` '
+                                 '(nvcc, sm_100a). hallthrusterpem_b200 has no CPU fallback.')
+        lib = ctypes.CDLL(str(path))
+        vp, i32, i64, dbl, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_uint32
+        dptr = ctypes.POINTER(ctypes.c_double)
+        lib.hpem_abi_version.restype = i32
+        lib.hpem_last_error.restype = ctypes.c_char_p
+        lib.hpem_launch_count.restype = i64
+        lib.hpem_grid_create.argtypes = [i32, i32, dptr, dptr, dptr, i32, dptr, ctypes.POINTER(vp)]
+        lib.hpem_grid_create.restype = i32
+        lib.hpem_grid_destroy.argtypes = [vp]
+        lib.hpem_grid_destroy.restype = i32
+        lib.hpem_grid_is_uniform.argtypes = [vp]
+        lib.hpem_grid_is_uniform.restype = i32
+        lib.hpem_eval.argtypes = [vp, i64, ctypes.POINTER(HpemInputs), ctypes.POINTER(HpemOutputs), dbl, u32, vp]
+        lib.hpem_eval.restype = i32
+        lib.hpem_eval_host.argtypes = [vp, i64, ctypes.POINTER(HpemInputs), ctypes.POINTER(HpemOutputs), dbl, u32]
+        lib.hpem_eval_host.restype = i32
+        if lib.hpem_abi_version() != 1:
+            raise HpemError(f'libhpem ABI version {lib.hpem_abi_version()} != 1')
+        _lib = lib
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != HPEM_OK:
+        msg = load().hpem_last_error().decode('utf-8', 'replace')
+        raise HpemError(f'libhpem status {status}: {msg}')

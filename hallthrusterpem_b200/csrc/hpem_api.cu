@@ -1,0 +1,388 @@
+// hpem_api.cu -- C ABI of libhpem (see include/hpem.h).  Host side: argument checking, grid handle,
+// kernel dispatch, and the host-buffer pipeline (H2D -> kernel -> D2H, chunked over samples).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/hpem.h"
+#include "hpem_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define HPEM_CUDA(call)                                                                            \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(HPEM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Which inputs each output group reads (cathode.py:26-31, plume.py:40-49)
+constexpr int kCathodeInputs[] = {HPEM_IN_P_b, HPEM_IN_V_a, HPEM_IN_T_e, HPEM_IN_V_vac, HPEM_IN_Pstar, HPEM_IN_P_T};
+constexpr int kPlumeInputs[] = {HPEM_IN_P_b, HPEM_IN_c0, HPEM_IN_c1, HPEM_IN_c2, HPEM_IN_c3,
+                                HPEM_IN_c4,  HPEM_IN_c5, HPEM_IN_sigma_cex, HPEM_IN_I_B0};
+
+struct Workspace {
+    std::mutex mu;
+    double* d_in[HPEM_N_INPUTS] = {};
+    size_t in_cap = 0;  // samples
+    double* d_small[4] = {};  // V_cc, div_angle, T_c, cos_div
+    size_t small_cap = 0;     // elements (n * R)
+    uint8_t* d_invalid = nullptr;
+    size_t invalid_cap = 0;
+    double* d_j = nullptr;
+    size_t j_cap = 0;  // elements
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    std::vector<cudaEvent_t> events;
+};
+
+}  // namespace
+
+struct hpem_grid {
+    int device = 0;
+    int n_angles = 0, n_angles_pad = 0, n_radii = 0;
+    bool uniform = false;
+    double h = 0.0, radius0 = 1.0;
+    double2* d_w = nullptr;
+    double* d_alpha = nullptr;
+    double* d_radii = nullptr;
+    size_t smem_uniform = 0;
+    bool smem_ok = false;
+    Workspace ws;
+};
+
+namespace {
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        HPEM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+    return HPEM_OK;
+}
+
+bool wants_plume(const hpem_outputs& o) {
+    return o.j_ion || o.div_angle || o.T_c || o.cos_div || o.invalid;
+}
+
+// Fill EvalParams for samples [first, first+count) of device-resident inputs/outputs.
+void fill_params(const hpem_grid& g, const hpem_inputs& in, const hpem_outputs& out, int64_t first, int64_t count,
+                 double torr, hpem::EvalParams& p) {
+    for (int k = 0; k < HPEM_N_INPUTS; ++k) {
+        p.in[k] = in.ptr[k] ? in.ptr[k] + first : nullptr;
+        p.scalar[k] = in.scalar[k];
+    }
+    p.n = count;
+    p.torr = torr;
+    const int64_t R = g.n_radii;
+    p.v_cc = out.V_cc ? out.V_cc + first : nullptr;
+    p.j_ion = out.j_ion ? out.j_ion + first * g.n_angles * R : nullptr;
+    p.div_angle = out.div_angle ? out.div_angle + first * R : nullptr;
+    p.t_c = out.T_c ? out.T_c + first * R : nullptr;
+    p.cos_div = out.cos_div ? out.cos_div + first * R : nullptr;
+    p.invalid = out.invalid ? out.invalid + first : nullptr;
+    p.n_angles = g.n_angles;
+    p.n_angles_pad = g.n_angles_pad;
+    p.n_radii = g.n_radii;
+    p.w = g.d_w;
+    p.alpha = g.d_alpha;
+    p.radii = g.d_radii;
+    p.h = g.h;
+    p.radius0 = g.radius0;
+    p.has_thrust = out.T_c != nullptr;
+}
+
+int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store_j, uint32_t flags, cudaStream_t st) {
+    using namespace hpem;
+    if (p.n <= 0) return HPEM_OK;
+    const bool use_uniform = g.uniform && g.n_radii == 1 && g.smem_ok && !(flags & HPEM_FLAG_FORCE_DIRECT);
+    if (use_uniform || !plume) {
+        const unsigned blocks = (unsigned)((p.n + kThreadsU - 1) / kThreadsU);
+        const size_t smem = plume ? g.smem_uniform : 0;
+        if (!plume)
+            eval_uniform_kernel<false, false><<<blocks, kThreadsU, 0, st>>>(p);
+        else if (store_j)
+            eval_uniform_kernel<true, true><<<blocks, kThreadsU, smem, st>>>(p);
+        else
+            eval_uniform_kernel<true, false><<<blocks, kThreadsU, smem, st>>>(p);
+    } else {
+        const unsigned blocks = (unsigned)((p.n + kWarpsD - 1) / kWarpsD);
+        eval_direct_kernel<true><<<blocks, kThreadsD, 0, st>>>(p);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    HPEM_CUDA(cudaGetLastError());
+    return HPEM_OK;
+}
+
+int check_request(const hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_outputs* out) {
+    if (!g) return fail(HPEM_ERR_INVALID_ARG, "grid handle is NULL");
+    if (!in || !out) return fail(HPEM_ERR_INVALID_ARG, "inputs/outputs struct is NULL");
+    if (n < 0) return fail(HPEM_ERR_INVALID_ARG, "negative sample count %lld", (long long)n);
+    if (n > (int64_t)2147483647 * 64) return fail(HPEM_ERR_INVALID_ARG, "sample count %lld too large for one call", (long long)n);
+    if (!out->V_cc && !wants_plume(*out)) return fail(HPEM_ERR_INVALID_ARG, "no output requested");
+    return HPEM_OK;
+}
+
+template <typename T>
+int grow(T*& ptr, size_t& cap, size_t need) {
+    if (need <= cap) return HPEM_OK;
+    if (ptr) HPEM_CUDA(cudaFree(ptr));
+    ptr = nullptr;
+    cap = 0;
+    const size_t want = need + need / 8;
+    HPEM_CUDA(cudaMalloc((void**)&ptr, want * sizeof(T)));
+    cap = want;
+    return HPEM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hpem_abi_version(void) { return HPEM_ABI_VERSION; }
+
+const char* hpem_last_error(void) { return g_err; }
+
+int64_t hpem_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int hpem_grid_create(int device, int n_angles, const double* alpha, const double* wd, const double* wn, int n_radii,
+                     const double* radii, hpem_grid** out) {
+    if (!out) return fail(HPEM_ERR_INVALID_ARG, "out handle pointer is NULL");
+    *out = nullptr;
+    if (n_angles < 2 || n_angles > 8192) return fail(HPEM_ERR_INVALID_ARG, "n_angles must be in [2, 8192], got %d", n_angles);
+    if (n_radii < 1 || n_radii > 4096) return fail(HPEM_ERR_INVALID_ARG, "n_radii must be in [1, 4096], got %d", n_radii);
+    if (!alpha || !wd || !wn || !radii) return fail(HPEM_ERR_INVALID_ARG, "alpha/wd/wn/radii must be non-NULL host arrays");
+    int ndev = 0;
+    HPEM_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(HPEM_ERR_INVALID_ARG, "device %d out of range (%d visible)", device, ndev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", device);
+
+    hpem_grid* g = new (std::nothrow) hpem_grid();
+    if (!g) return fail(HPEM_ERR_CUDA, "out of host memory");
+    g->device = device;
+    g->n_angles = n_angles;
+    g->n_angles_pad = (n_angles + hpem::kChunk - 1) / hpem::kChunk * hpem::kChunk;
+    g->n_radii = n_radii;
+    g->radius0 = radii[0];
+    g->h = alpha[1];
+    // uniform <=> alpha[i] == i*alpha[1] to rounding (np.linspace(0, pi/2, A), plume.py:53)
+    bool uni = (alpha[0] == 0.0) && (alpha[1] > 0.0);
+    for (int i = 2; i < n_angles && uni; ++i) {
+        const double want = double(i) * alpha[1];
+        if (!(std::fabs(alpha[i] - want) <= 4.0 * 2.220446049250313e-16 * std::fabs(want))) uni = false;
+    }
+    g->uniform = uni;
+
+    std::vector<double2> w(g->n_angles_pad);
+    for (int i = 0; i < g->n_angles_pad; ++i) w[i] = (i < n_angles) ? make_double2(wd[i], wn[i]) : make_double2(0.0, 0.0);
+
+    auto cleanup = [&](int rc) {
+        hpem_grid_destroy(g);
+        return rc;
+    };
+#define HPEM_CUDA_G(call)                                                                                    \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return cleanup(fail(HPEM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)));             \
+    } while (0)
+    HPEM_CUDA_G(cudaMalloc((void**)&g->d_w, w.size() * sizeof(double2)));
+    HPEM_CUDA_G(cudaMalloc((void**)&g->d_alpha, n_angles * sizeof(double)));
+    HPEM_CUDA_G(cudaMalloc((void**)&g->d_radii, n_radii * sizeof(double)));
+    HPEM_CUDA_G(cudaMemcpy(g->d_w, w.data(), w.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    HPEM_CUDA_G(cudaMemcpy(g->d_alpha, alpha, n_angles * sizeof(double), cudaMemcpyHostToDevice));
+    HPEM_CUDA_G(cudaMemcpy(g->d_radii, radii, n_radii * sizeof(double), cudaMemcpyHostToDevice));
+#undef HPEM_CUDA_G
+
+    g->smem_uniform = size_t(g->n_angles_pad) * sizeof(double2) + size_t(hpem::kWarpsU) * 32 * hpem::kTilePitch * sizeof(double);
+    g->smem_ok = g->smem_uniform <= 200 * 1024;
+    if (g->smem_ok) {
+        int rc = set_smem(hpem::eval_uniform_kernel<true, true>, g->smem_uniform);
+        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, false>, g->smem_uniform);
+        if (rc != HPEM_OK) return cleanup(rc);
+    }
+    *out = g;
+    return HPEM_OK;
+}
+
+int hpem_grid_destroy(hpem_grid* g) {
+    if (!g) return HPEM_OK;
+    DeviceGuard guard(g->device);
+    Workspace& ws = g->ws;
+    for (auto& p : ws.d_in) if (p) cudaFree(p);
+    for (auto& p : ws.d_small) if (p) cudaFree(p);
+    if (ws.d_invalid) cudaFree(ws.d_invalid);
+    if (ws.d_j) cudaFree(ws.d_j);
+    for (auto e : ws.events) cudaEventDestroy(e);
+    if (ws.s_compute) cudaStreamDestroy(ws.s_compute);
+    if (ws.s_copy) cudaStreamDestroy(ws.s_copy);
+    if (g->d_w) cudaFree(g->d_w);
+    if (g->d_alpha) cudaFree(g->d_alpha);
+    if (g->d_radii) cudaFree(g->d_radii);
+    delete g;
+    return HPEM_OK;
+}
+
+int hpem_grid_is_uniform(const hpem_grid* g) {
+    if (!g) return fail(HPEM_ERR_INVALID_ARG, "grid handle is NULL");
+    return (g->uniform && g->smem_ok) ? 1 : 0;
+}
+
+int hpem_eval(const hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_outputs* out, double torr_2_pa,
+              uint32_t flags, void* stream) {
+    int rc = check_request(g, n, in, out);
+    if (rc != HPEM_OK) return rc;
+    const bool plume = wants_plume(*out);
+    DeviceGuard guard(g->device);
+    if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", g->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // one launch covers at most 2^31-1 blocks; split huge batches
+    const int64_t max_per_launch = (int64_t)1 << 30;
+    for (int64_t first = 0; first < n; first += max_per_launch) {
+        const int64_t count = std::min(max_per_launch, n - first);
+        hpem::EvalParams p;
+        fill_params(*g, *in, *out, first, count, torr_2_pa, p);
+        rc = launch(*g, p, plume, out->j_ion != nullptr, flags, st);
+        if (rc != HPEM_OK) return rc;
+    }
+    return HPEM_OK;
+}
+
+int hpem_eval_host(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_outputs* out, double torr_2_pa,
+                   uint32_t flags) {
+    int rc = check_request(g, n, in, out);
+    if (rc != HPEM_OK) return rc;
+    if (n == 0) return HPEM_OK;
+    const bool plume = wants_plume(*out);
+    DeviceGuard guard(g->device);
+    if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", g->device);
+    Workspace& ws = g->ws;
+    std::lock_guard<std::mutex> lock(ws.mu);
+    if (!ws.s_compute) HPEM_CUDA(cudaStreamCreateWithFlags(&ws.s_compute, cudaStreamNonBlocking));
+    if (!ws.s_copy) HPEM_CUDA(cudaStreamCreateWithFlags(&ws.s_copy, cudaStreamNonBlocking));
+
+    const int64_t A = g->n_angles, R = g->n_radii;
+    // which inputs are needed
+    bool need[HPEM_N_INPUTS] = {};
+    if (out->V_cc) for (int k : kCathodeInputs) need[k] = true;
+    if (plume) for (int k : kPlumeInputs) need[k] = true;
+    if (out->T_c) need[HPEM_IN_T] = true;
+
+    // super-batches bound the device footprint of j_ion (default cap 16 GiB of the 180 GB HBM)
+    const int64_t row_elems = A * R;
+    const int64_t cap_elems = ((int64_t)16 << 30) / 8;
+    const int64_t batch = out->j_ion ? std::max<int64_t>(1, std::min<int64_t>(n, cap_elems / row_elems)) : n;
+    // D2H chunks of ~32 MiB so the copy engine starts as soon as the first rows exist
+    const int64_t chunk = out->j_ion ? std::max<int64_t>(1024, ((int64_t)32 << 20) / (row_elems * 8)) : batch;
+
+    for (int64_t b0 = 0; b0 < n; b0 += batch) {
+        const int64_t nb = std::min(batch, n - b0);
+        hpem_inputs din = *in;
+        for (int k = 0; k < HPEM_N_INPUTS; ++k) din.ptr[k] = nullptr;
+        // (re)allocate inputs with one common capacity
+        if ((size_t)nb > ws.in_cap) {
+            for (int k = 0; k < HPEM_N_INPUTS; ++k) {
+                if (ws.d_in[k]) { cudaFree(ws.d_in[k]); ws.d_in[k] = nullptr; }
+            }
+            ws.in_cap = (size_t)nb + (size_t)nb / 8;
+        }
+        for (int k = 0; k < HPEM_N_INPUTS; ++k) {
+            if (!need[k] || !in->ptr[k]) continue;
+            if (!ws.d_in[k]) HPEM_CUDA(cudaMalloc((void**)&ws.d_in[k], ws.in_cap * sizeof(double)));
+            din.ptr[k] = ws.d_in[k];
+        }
+        hpem_outputs dout = {};
+        double* host_small[4] = {out->V_cc, out->div_angle, out->T_c, out->cos_div};
+        const size_t small_elems[4] = {(size_t)nb, (size_t)(nb * R), (size_t)(nb * R), (size_t)(nb * R)};
+        const size_t small_need = (size_t)(nb * R);
+        if (small_need > ws.small_cap) {
+            for (auto& p : ws.d_small) if (p) { cudaFree(p); p = nullptr; }
+            ws.small_cap = small_need + small_need / 8;
+        }
+        double** dsmall_out[4] = {&dout.V_cc, &dout.div_angle, &dout.T_c, &dout.cos_div};
+        for (int q = 0; q < 4; ++q) {
+            if (!host_small[q]) continue;
+            if (!ws.d_small[q]) HPEM_CUDA(cudaMalloc((void**)&ws.d_small[q], ws.small_cap * sizeof(double)));
+            *dsmall_out[q] = ws.d_small[q];
+        }
+        if (out->invalid) {
+            rc = grow(ws.d_invalid, ws.invalid_cap, (size_t)nb);
+            if (rc != HPEM_OK) return rc;
+            dout.invalid = ws.d_invalid;
+        }
+        if (out->j_ion) {
+            rc = grow(ws.d_j, ws.j_cap, (size_t)(nb * row_elems));
+            if (rc != HPEM_OK) return rc;
+            dout.j_ion = ws.d_j;
+        }
+
+        // H2D of the per-sample inputs (compute stream, in order before the kernels)
+        for (int k = 0; k < HPEM_N_INPUTS; ++k) {
+            if (!din.ptr[k]) continue;
+            HPEM_CUDA(cudaMemcpyAsync(ws.d_in[k], in->ptr[k] + b0, (size_t)nb * sizeof(double), cudaMemcpyHostToDevice,
+                                      ws.s_compute));
+        }
+        const int64_t n_chunks = (nb + chunk - 1) / chunk;
+        while ((int64_t)ws.events.size() < n_chunks) {
+            cudaEvent_t e;
+            HPEM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ws.events.push_back(e);
+        }
+        for (int64_t c = 0; c < n_chunks; ++c) {
+            const int64_t first = c * chunk, count = std::min(chunk, nb - first);
+            hpem::EvalParams p;
+            fill_params(*g, din, dout, first, count, torr_2_pa, p);
+            rc = launch(*g, p, plume, dout.j_ion != nullptr, flags, ws.s_compute);
+            if (rc != HPEM_OK) return rc;
+            if (out->j_ion) {
+                HPEM_CUDA(cudaEventRecord(ws.events[c], ws.s_compute));
+                HPEM_CUDA(cudaStreamWaitEvent(ws.s_copy, ws.events[c], 0));
+                HPEM_CUDA(cudaMemcpyAsync(out->j_ion + (b0 + first) * row_elems, ws.d_j + first * row_elems,
+                                          (size_t)(count * row_elems) * sizeof(double), cudaMemcpyDeviceToHost, ws.s_copy));
+            }
+        }
+        for (int q = 0; q < 4; ++q) {
+            if (!host_small[q]) continue;
+            const int64_t per = (q == 0) ? 1 : R;
+            HPEM_CUDA(cudaMemcpyAsync(host_small[q] + b0 * per, ws.d_small[q], small_elems[q] * sizeof(double),
+                                      cudaMemcpyDeviceToHost, ws.s_compute));
+        }
+        if (out->invalid)
+            HPEM_CUDA(cudaMemcpyAsync(out->invalid + b0, ws.d_invalid, (size_t)nb, cudaMemcpyDeviceToHost, ws.s_compute));
+        HPEM_CUDA(cudaStreamSynchronize(ws.s_compute));
+        HPEM_CUDA(cudaStreamSynchronize(ws.s_copy));
+    }
+    return HPEM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+"""Host side of the plume + cathode path: broadcasting, buffer carriers, grid handles, C-ABI calls.
+
+Mirrors the calling convention of the reference's model functions
+(/root/reference/src/hallmd/models/plume.py:21, cathode.py:16): a dict of named inputs (Python scalars, NumPy
+arrays of any common loop shape, or -- new -- torch CUDA float64 tensors) in, a dict of outputs out.
+
+* host inputs  -> `hpem_eval_host` (chunked H2D / kernel / D2H pipeline inside the library) -> NumPy outputs
+  (backed by pinned memory so the D2H DMA goes straight into the returned arrays);
+* torch CUDA inputs -> `hpem_eval` on torch's current stream, zero-copy via `data_ptr()` -> torch CUDA outputs.
+
+PyTorch is only the buffer carrier (device allocations, pinned host memory, streams).  All arithmetic happens
+in libhpem's CUDA kernels; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from typing import Any
+
+import numpy as np
+
+from . import _lib
+from .quadrature import angle_grid, fused_weights
+
+DEFAULT_TORR_2_PA = 133.322
+"""pem_core.constants.TORR_2_PA is not vendored with the reference (uv.lock:1655-1657); 133.322 is the value hallmd
+used historically.  If `pem_core` is importable its value is used instead (see `torr_2_pa()`)."""
+
+_PIN_THRESHOLD_BYTES = 1 << 20
+
+
+def torr_2_pa() -> float:
+    try:  # the real dependency, when present, is authoritative
+        from pem_core.constants import TORR_2_PA  # type: ignore
+        return float(TORR_2_PA)
+    except Exception:
+        return DEFAULT_TORR_2_PA
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _is_torch_tensor(x: Any) -> bool:
+    return type(x).__module__.startswith('torch') and hasattr(x, 'data_ptr')
+
+
+# ----------------------------------------------------------------------------------------------
+# grid handles (angle grid + fused weights + radii live on the device, cached per (device, A, radii))
+# ----------------------------------------------------------------------------------------------
+class GridHandle:
+    def __init__(self, device: int, n_angles: int, radii: np.ndarray, alpha: np.ndarray | None = None):
+        lib = _lib.load()
+        self.device = int(device)
+        self.alpha = angle_grid(n_angles) if alpha is None else np.ascontiguousarray(alpha, dtype=np.float64)
+        self.alpha.setflags(write=False)
+        self.n_angles = int(self.alpha.shape[0])
+        self.radii = np.ascontiguousarray(radii, dtype=np.float64).reshape(-1)
+        self.n_radii = int(self.radii.shape[0])
+        wd, wn = fused_weights(self.alpha)
+        dptr = ctypes.POINTER(ctypes.c_double)
+        handle = ctypes.c_void_p()
+        _lib.check(lib.hpem_grid_create(self.device, self.n_angles, self.alpha.ctypes.data_as(dptr),
+                                        wd.ctypes.data_as(dptr), wn.ctypes.data_as(dptr), self.n_radii,
+                                        self.radii.ctypes.data_as(dptr), ctypes.byref(handle)))
+        self._h = handle
+        self.uniform = bool(lib.hpem_grid_is_uniform(handle))
+        self.host_lock = threading.Lock()
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        return self._h
+
+    def close(self):
+        if self._h:
+            _lib.load().hpem_grid_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_grid_cache: dict[tuple, GridHandle] = {}
+_grid_lock = threading.Lock()
+
+
+def get_grid(device: int, n_angles: int, radii: np.ndarray) -> GridHandle:
+    radii = np.ascontiguousarray(np.atleast_1d(radii), dtype=np.float64)
+    key = (int(device), int(n_angles), radii.tobytes())
+    with _grid_lock:
+        g = _grid_cache.get(key)
+        if g is None:
+            if len(_grid_cache) >= 64:
+                _grid_cache.pop(next(iter(_grid_cache))).close()
+            g = _grid_cache[key] = GridHandle(device, n_angles, radii)
+        return g
+
+
+# ----------------------------------------------------------------------------------------------
+# input marshalling
+# ----------------------------------------------------------------------------------------------
+class _Batch:
+    """Broadcast the named inputs to a common loop shape and build the hpem_inputs struct."""
+
+    def __init__(self, inputs: dict, names: tuple[str, ...], optional: tuple[str, ...] = ()):
+        vals = {}
+        for name in names:
+            vals[name] = inputs[name]                     # KeyError for a missing key, like the reference
+        for name in optional:
+            if inputs.get(name, None) is not None:
+                vals[name] = inputs[name]
+        self.on_device = any(_is_torch_tensor(v) and v.is_cuda for v in vals.values())
+        self.device_index = None
+        if self.on_device:
+            devs = {v.device.index for v in vals.values() if _is_torch_tensor(v) and v.is_cuda}
+            if len(devs) != 1:
+                raise ValueError(f'inputs live on several CUDA devices: {sorted(devs)}')
+            self.device_index = devs.pop()
+        shapes = [tuple(v.shape) if hasattr(v, 'shape') else () for v in vals.values()]
+        self.loop_shape = tuple(np.broadcast_shapes(*shapes)) if shapes else ()
+        self.out_shape = self.loop_shape if len(self.loop_shape) > 0 else (1,)   # np.atleast_1d (plume.py:59)
+        self.n = int(np.prod(self.out_shape, dtype=np.int64))
+        self.struct = _lib.HpemInputs()
+        self._keep = []                                   # keep converted buffers alive during the call
+        for name, v in vals.items():
+            k = _lib.INPUT_NAMES.index(name)
+            size = int(np.prod(v.shape, dtype=np.int64)) if hasattr(v, 'shape') else 1
+            if size == 1:                                 # NumPy scalar broadcasting (test_plume.py:67-77)
+                self.struct.ptr[k] = None
+                self.struct.scalar[k] = float(v.reshape(-1)[0]) if hasattr(v, 'shape') else float(v)
+                continue
+            if self.on_device:
+                torch = _torch()
+                t = v if _is_torch_tensor(v) else torch.as_tensor(np.asarray(v, dtype=np.float64))
+                t = t.to(device=f'cuda:{self.device_index}', dtype=torch.float64)
+                if tuple(t.shape) != self.out_shape:
+                    t = t.broadcast_to(self.out_shape)
+                t = t.contiguous()
+                self._keep.append(t)
+                self.struct.ptr[k] = t.data_ptr()
+            else:
+                a = v.detach().cpu().numpy() if _is_torch_tensor(v) else np.asarray(v)
+                a = np.asarray(a, dtype=np.float64)
+                if a.shape != self.out_shape:
+                    a = np.broadcast_to(a, self.out_shape)
+                a = np.ascontiguousarray(a)
+                self._keep.append(a)
+                self.struct.ptr[k] = a.ctypes.data
+        self.present = set(vals)
+
+
+def _alloc_host(shape: tuple[int, ...], dtype=np.float64) -> np.ndarray:
+    """Host output buffer; large ones are page-locked (through torch's caching host allocator, so repeated
+    calls reuse the registration) and the D2H copy DMAs straight into the array that is returned."""
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    if nbytes >= _PIN_THRESHOLD_BYTES:
+        torch = _torch()
+        tdtype = torch.float64 if np.dtype(dtype) == np.float64 else torch.uint8
+        return torch.empty(shape, dtype=tdtype, pin_memory=True).numpy()
+    return np.empty(shape, dtype=dtype)
+
+
+def evaluate(inputs: dict, *, want_cathode: bool, want_plume: bool, sweep_radius=1.0, n_angles: int = 91,
+             torr: float | None = None, device: int | None = None, direct: bool = False,
+             want_j_ion: bool = True, extras: bool = False) -> dict:
+    """Run the fused kernel for the requested output groups.  Returns raw outputs keyed like the reference."""
+    lib = _lib.load()
+    names: tuple[str, ...] = ()
+    if want_cathode:
+        names += _lib.CATHODE_INPUTS
+    if want_plume:
+        names += tuple(k for k in _lib.PLUME_INPUTS if k not in names)
+    batch = _Batch(inputs, names, optional=('T',) if want_plume else ())
+    has_thrust = 'T' in batch.present
+    torr = torr_2_pa() if torr is None else float(torr)
+
+    radii = np.atleast_1d(np.asarray(sweep_radius, dtype=np.float64)).reshape(-1)
+    n_radii = int(radii.shape[0])
+    single = n_radii == 1                                  # plume.py:130 squeezes the radius axis
+
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError('hallthrusterpem_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    if batch.on_device:
+        dev = batch.device_index
+    else:
+        dev = torch.cuda.current_device() if device is None else int(device)
+    grid = get_grid(dev, n_angles, radii) if want_plume else get_grid(dev, 91, np.array([1.0]))
+
+    loop = batch.out_shape
+    rshape = loop if single else loop + (n_radii,)
+    jshape = loop + (grid.n_angles,) if single else loop + (grid.n_angles, n_radii)
+    out = _lib.HpemOutputs()
+    result: dict[str, Any] = {}
+
+    def new(shape, dtype=np.float64):
+        if batch.on_device:
+            tdtype = torch.float64 if dtype == np.float64 else torch.uint8
+            t = torch.empty(shape, dtype=tdtype, device=f'cuda:{dev}')
+            return t, t.data_ptr()
+        a = _alloc_host(shape, dtype)
+        return a, a.ctypes.data
+
+    if want_cathode:
+        result['V_cc'], out.V_cc = new(loop)
+    if want_plume:
+        if want_j_ion:
+            result['j_ion'], out.j_ion = new(jshape)
+        result['div_angle'], out.div_angle = new(rshape)
+        if has_thrust:
+            result['T_c'], out.T_c = new(rshape)
+        if extras:
+            result['cos_div'], out.cos_div = new(rshape)
+            result['invalid'], out.invalid = new(loop, np.uint8)
+
+    flags = _lib.FLAG_FORCE_DIRECT if direct else 0
+    if batch.on_device:
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.hpem_eval(grid.handle, batch.n, ctypes.byref(batch.struct), ctypes.byref(out), torr,
+                                     flags, ctypes.c_void_p(stream)))
+    else:
+        _lib.check(lib.hpem_eval_host(grid.handle, batch.n, ctypes.byref(batch.struct), ctypes.byref(out), torr,
+                                      flags))
+    if want_plume:
+        coords = np.empty(loop, dtype=object)              # plume.py:152-157 (C-speed fill, same ndarray object)
+        coords.fill(grid.alpha)
+        result['j_ion_coords'] = coords
+    return result

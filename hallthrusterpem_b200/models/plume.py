@@ -1,0 +1,36 @@
+"""Plume model -- drop-in for `hallmd.models.plume.current_density`
+(/root/reference/src/hallmd/models/plume.py:21-159), evaluated by libhpem's CUDA kernels."""
+from __future__ import annotations
+
+from ..engine import evaluate
+
+__all__ = ['current_density', 'plume_cathode']
+
+
+def current_density(inputs: dict, sweep_radius=1.0, *, n_angles: int = 91, torr_2_pa: float | None = None,
+                    device: int | None = None, direct: bool = False, extras: bool = False) -> dict:
+    """Semi-empirical ion current density (j_ion) plume model over a 90 deg sweep (0 deg = thruster centerline),
+    plus the plume divergence angle and, if `T` is given, the divergence-corrected thrust.
+
+    :param inputs: `P_b`, `c0`, `c1`, `c2`, `c3`, `c4`, `c5`, `sigma_cex`, `I_B0` (and optionally `T`): Python
+                   scalars, NumPy arrays of a common (broadcastable) loop shape, or torch CUDA float64 tensors.
+    :param sweep_radius: radius/radii (m) of the sweep; with several radii `j_ion` gains a trailing radius axis.
+    :param n_angles: number of sweep angles (keyword-only extra; the reference hard-codes 91, plume.py:53).
+    :param torr_2_pa: value of `pem_core.constants.TORR_2_PA` (keyword-only extra).
+    :param device: CUDA device index for host inputs (keyword-only extra).
+    :param direct: force the reference-operation-order kernel instead of the recurrence kernel (diagnostics).
+    :param extras: also return `cos_div` and the whole-sample `invalid` mask (plume.py:105,124).
+    :returns outputs: `j_ion` (..., A[, R]), `div_angle` (...[, R]), optionally `T_c`, and `j_ion_coords`
+                      (object array of loop shape whose elements are the angle grid in radians).
+    """
+    return evaluate(inputs, want_cathode=False, want_plume=True, sweep_radius=sweep_radius, n_angles=n_angles,
+                    torr=torr_2_pa, device=device, direct=direct, extras=extras)
+
+
+def plume_cathode(inputs: dict, sweep_radius=1.0, *, n_angles: int = 91, torr_2_pa: float | None = None,
+                  device: int | None = None, direct: bool = False, extras: bool = False,
+                  want_j_ion: bool = True) -> dict:
+    """The PEM v0 chain Cathode -> (Thruster, external) -> Plume in ONE fused launch over the same samples
+    (pem_v0_SPT-100.yml:5,62,215): returns `V_cc` together with the plume outputs.  `P_b` is loaded once."""
+    return evaluate(inputs, want_cathode=True, want_plume=True, sweep_radius=sweep_radius, n_angles=n_angles,
+                    torr=torr_2_pa, device=device, direct=direct, extras=extras, want_j_ion=want_j_ion)

@@ -1,0 +1,222 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the committed golden vectors and the oracle.
+
+Every test here goes Python API -> ctypes -> libhpem.so -> sm_100a kernels.  The oracle (`oracle/`) is only the
+checker.  Tolerances are the ones documented in tests/parity.py (rel 1e-12 per BASELINE.json's north_star).
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted((Path(__file__).parent / 'golden').glob('*.npz'))
+
+
+def _models():
+    from hallthrusterpem_b200.models import cathode_coupling, current_density, plume_cathode
+    return cathode_coupling, current_density, plume_cathode
+
+
+def _compare(out, g, inputs, torr, radii, label):
+    frac = parity.check_j_ion(out['j_ion'], g['j_ion'], inputs['I_B0'], radii, g['invalid'], f'{label}:j_ion')
+    assert np.array_equal(np.asarray(out['invalid']).astype(bool), g['invalid']), f'{label}: invalid mask differs'
+    parity.check_rel(out['cos_div'], g['cos_div'], f'{label}:cos_div')
+    parity.check_rel(out['T_c'], g['T_c'], f'{label}:T_c')
+    parity.check_div_angle(out['div_angle'], g['div_angle'], out['cos_div'], g['cos_div'], f'{label}:div_angle')
+    if 'V_cc' in out:
+        parity.check_rel(out['V_cc'], g['V_cc'], f'{label}:V_cc', scale=parity.cathode_scale(inputs, torr))
+    return frac
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=[p.stem for p in GOLDEN])
+@pytest.mark.parametrize('direct', [False, True], ids=['fast', 'direct'])
+def test_golden_host_path(path, direct, cuda_device):
+    """NumPy in -> NumPy out (hpem_eval_host), both kernels, every golden file."""
+    _, _, plume_cathode = _models()
+    g, meta, inputs = parity.load_golden(path)
+    radii = g['sweep_radius']
+    sweep = float(radii[0]) if radii.shape[0] == 1 else radii
+    out = plume_cathode(inputs, sweep, n_angles=meta['n_angles'], torr_2_pa=meta['torr_2_pa'], direct=direct,
+                        extras=True)
+    assert isinstance(out['j_ion'], np.ndarray) and out['j_ion'].dtype == np.float64
+    frac = _compare(out, g, inputs, meta['torr_2_pa'], radii, path.stem)
+    assert frac > 0.98, f'only {frac:.4f} of j_ion meets the pure rel-1e-12 rule'
+    coords = out['j_ion_coords']
+    assert coords.dtype == object and coords.shape == g['div_angle'].shape[:1]
+    assert np.array_equal(coords[0], np.linspace(0, np.pi / 2, meta['n_angles']))
+
+
+@pytest.mark.parametrize('path', [p for p in GOLDEN if 'r25' not in p.stem and '_r3' not in p.stem],
+                         ids=lambda p: p.stem)
+def test_golden_device_path(path, cuda_device):
+    """torch CUDA tensors in -> torch CUDA tensors out (hpem_eval, zero-copy)."""
+    import torch
+    _, current_density, _ = _models()
+    g, meta, inputs = parity.load_golden(path)
+    dev_inputs = {k: torch.as_tensor(v, device='cuda:0') for k, v in inputs.items()}
+    out = current_density(dev_inputs, 1.0, n_angles=meta['n_angles'], torr_2_pa=meta['torr_2_pa'], extras=True)
+    assert out['j_ion'].is_cuda and out['j_ion'].dtype == torch.float64
+    host = {k: (v.cpu().numpy() if hasattr(v, 'cpu') else v) for k, v in out.items()}
+    _compare(host, g, inputs, meta['torr_2_pa'], g['sweep_radius'], path.stem + ':device')
+
+
+def test_separate_functions_match_fused(cuda_device):
+    """cathode_coupling / current_density called separately == the fused chain (same kernels, same bits)."""
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    cathode_coupling, current_density, plume_cathode = _models()
+    b = spt100_batch(5000, 77)
+    fused = plume_cathode(b, 1.0, n_angles=100)
+    v = cathode_coupling(b)
+    p = current_density(b, 1.0, n_angles=100)
+    assert np.array_equal(v['V_cc'], fused['V_cc'])
+    assert np.array_equal(p['j_ion'], fused['j_ion'])
+    assert np.array_equal(p['div_angle'], fused['div_angle'])
+    assert np.array_equal(p['T_c'], fused['T_c'])
+    assert set(p) == {'j_ion', 'div_angle', 'T_c', 'j_ion_coords'} and set(v) == {'V_cc'}
+
+
+@pytest.mark.parametrize('n,n_angles', [(1, 91), (31, 91), (33, 100), (1000, 100), (4097, 200), (20000, 256), (3000, 512),
+                                        (777, 17), (500, 16), (500, 15), (100, 2), (100, 3)])
+def test_against_oracle_seeded(n, n_angles, cuda_device):
+    """Seeded SPT-100 batches at sizes the oracle finishes in seconds (ragged warps, odd/even A, A % 16 != 0)."""
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    from oracle.ref_restated import cathode_coupling_oracle, current_density_oracle
+    _, _, plume_cathode = _models()
+    torr = 133.322
+    b = spt100_batch(n, 1000 + n + n_angles)
+    with np.errstate(all='ignore'):
+        ref = current_density_oracle(b, 1.0, n_angles, torr, with_coords=False, return_internals=True)
+        ref['V_cc'] = cathode_coupling_oracle(b, torr)['V_cc']
+    g = {'j_ion': ref['j_ion'], 'div_angle': ref['div_angle'], 'T_c': ref['T_c'], 'cos_div': ref['_cos_div'],
+         'invalid': ref['_invalid'], 'V_cc': ref['V_cc']}
+    for direct in (False, True):
+        out = plume_cathode(b, 1.0, n_angles=n_angles, torr_2_pa=torr, direct=direct, extras=True)
+        _compare(out, g, b, torr, np.array([1.0]), f'n{n}_a{n_angles}_{"direct" if direct else "fast"}')
+
+
+def test_fast_and_direct_kernels_agree_large(cuda_device):
+    """BASELINE config 2 size (1e6 x 200) on the device: the recurrence kernel against the direct kernel, which
+    evaluates the reference's expressions in the reference's order -- two independent implementations."""
+    import torch
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    _, current_density, _ = _models()
+    n, A = 1_000_000, 200
+    b = {k: torch.as_tensor(v, device='cuda:0') for k, v in spt100_batch(n, 2024).items()}
+    fast = current_density(b, 1.0, n_angles=A, extras=True)
+    direct = current_density(b, 1.0, n_angles=A, extras=True, direct=True)
+    jf, jd = fast['j_ion'], direct['j_ion']
+    rel = ((jf - jd).abs() / jd.abs()).max().item()
+    assert rel < 2e-13, rel
+    assert torch.equal(fast['invalid'], direct['invalid'])
+    assert ((fast['cos_div'] - direct['cos_div']).abs() / direct['cos_div'].abs()).max().item() < 1e-13
+    # size-independent property at full size: total current through the hemisphere is conserved (test_plume.py:90-98)
+    theta = torch.linspace(0, np.pi / 2, A, dtype=torch.float64, device='cuda:0')
+    from hallthrusterpem_b200.quadrature import simpson_weights
+    w = torch.as_tensor(simpson_weights(theta.cpu().numpy()), device='cuda:0')
+    current = 2 * np.pi * (jf * torch.sin(theta) * w).sum(-1)
+    ratio = current / b['I_B0']
+    wide = torch.as_tensor(fast['div_angle']) > 0.05         # Simpson on A=200 points cannot resolve needle beams
+    assert (ratio[wide] - 1).abs().max().item() < 5e-3
+
+
+def test_reference_unit_tests_restated(cuda_device):
+    """The bodies of the reference's own tests (tests/test_plume.py:17-98, tests/test_cathode.py:8-31), seeded."""
+    from scipy.integrate import simpson
+    cathode_coupling, current_density, _ = _models()
+    rng = np.random.default_rng(5)
+    N = 100
+    inputs_rand = {
+        'P_b': 10 ** (rng.random(N) * 4 - 8), 'c0': rng.random(N) * 0.8 + 0.1, 'c1': rng.random(N) * 0.8 + 0.1,
+        'c2': rng.random(N) * 30 - 15, 'c3': rng.random(N) + 0.1, 'c4': 10 ** (rng.random(N) * 4 + 18),
+        'c5': 10 ** (rng.random(N) * 4 + 14), 'sigma_cex': rng.random(N) * 7e-20 + 51e-20, 'I_B0': rng.random(N) * 6 + 2,
+    }
+    r_p = rng.random(25) * 0.2 + 1
+    out = current_density(inputs_rand, sweep_radius=r_p)
+    assert out['j_ion'].shape == (N, 91, 25)
+    assert out['div_angle'].shape == (N, 25) and 'T_c' not in out
+    assert np.min(out['j_ion']) >= 0 and np.max(out['j_ion']) <= 5e3
+
+    sweep = {'P_b': 10 ** (np.linspace(-6, -4, N)), 'c0': 0.1, 'c1': 0.7, 'c2': -8.0, 'c3': 0.2, 'c4': 1e20, 'c5': 1e16,
+             'sigma_cex': 55e-20, 'I_B0': 3}
+    out = current_density(sweep, sweep_radius=1)
+    j = out['j_ion']
+    assert j.shape == (N, 91) and np.min(j) >= 0 and np.max(j) <= 5e3
+    theta = np.linspace(0, np.pi / 2, j.shape[-1])
+    current = np.array([2 * np.pi * simpson(j[i, :] * np.sin(theta), x=theta) for i in range(N)])
+    err = np.sqrt(np.sum((current - np.mean(current)) ** 2) / np.sum(current ** 2))
+    assert err < 1e-4
+
+    scalar = cathode_coupling({'P_b': 10e-6, 'V_a': 300, 'T_e': 3, 'V_vac': 30, 'Pstar': 20e-6, 'P_T': 50e-6})
+    assert scalar['V_cc'].shape == (1,) and abs(scalar['V_cc'][0] - 30.11839324) < 1e-7
+    rand = {'P_b': 10 ** (rng.random(N) * 4 - 8), 'V_a': rng.random(N) * 200 + 200, 'T_e': rng.random(N) * 4 + 1,
+            'V_vac': rng.random(N) * 60, 'Pstar': rng.random(N) * 90e-6 + 10e-6, 'P_T': rng.random(N) * 90e-6 + 10e-6}
+    v = cathode_coupling(rand)['V_cc']
+    assert np.all(v >= 0) and np.all(v <= 100)
+    sw = {'P_b': 10 ** (np.linspace(-6, -4, N)), 'V_a': 300, 'T_e': 1.33, 'V_vac': 31.6, 'Pstar': 24.6e-6, 'P_T': 10.2e-6}
+    v = cathode_coupling(sw)['V_cc']
+    assert v.shape == (N,) and np.all(v >= 0) and np.all(v <= 100)
+
+
+def test_shapes_and_broadcasting(cuda_device):
+    """Output shapes of the reference (SURVEY.md section 8a 'verified shapes')."""
+    from oracle.ref_restated import current_density_oracle
+    _, current_density, _ = _models()
+    scal = {'P_b': 1e-5, 'c0': .1, 'c1': .7, 'c2': -8., 'c3': .2, 'c4': 1e20, 'c5': 1e16, 'sigma_cex': 55e-20, 'I_B0': 3,
+            'T': .08}
+    o = current_density(scal)
+    assert o['j_ion'].shape == (1, 91) and o['div_angle'].shape == (1,) and o['T_c'].shape == (1,)
+    assert o['j_ion_coords'].shape == (1,) and o['j_ion_coords'].dtype == object
+    assert abs(o['j_ion'][0, 0] - 23.5475585) < 1e-6 and abs(o['div_angle'][0] - 0.19785857) < 1e-8
+
+    rng = np.random.default_rng(9)
+    loop = dict(scal)
+    loop['P_b'] = 10 ** rng.uniform(-7, -4, (4, 3))
+    loop['c3'] = rng.uniform(0.2, 1.0, (4, 1))           # partial shape, broadcast against (4, 3)
+    loop['T'] = rng.uniform(0.02, 0.1, (4, 3))
+    o = current_density(loop, sweep_radius=[1.0, 1.5])
+    assert o['j_ion'].shape == (4, 3, 91, 2) and o['div_angle'].shape == (4, 3, 2) and o['T_c'].shape == (4, 3, 2)
+    assert o['j_ion_coords'].shape == (4, 3)
+    with np.errstate(all='ignore'):
+        ref = current_density_oracle(loop, [1.0, 1.5], 91, 133.322, with_coords=False, return_internals=True)
+    parity.check_j_ion(o['j_ion'], ref['j_ion'], 3.0, np.array([1.0, 1.5]), ref['_invalid'])
+    parity.check_rel(o['T_c'], ref['T_c'], 'T_c')
+
+    with pytest.raises(KeyError):
+        current_density({k: v for k, v in scal.items() if k != 'c4'})
+    with pytest.raises(ValueError):
+        current_density(dict(scal, P_b=np.ones(3), c0=np.ones(4)))
+
+
+def test_c_abi_error_reporting(cuda_device):
+    """API misuse returns a status + message, never crashes and never changes numeric conventions."""
+    import ctypes
+    from hallthrusterpem_b200 import _lib
+    lib = _lib.load()
+    handle = ctypes.c_void_p()
+    dptr = ctypes.POINTER(ctypes.c_double)
+    a = np.linspace(0, 1, 4)
+    rc = lib.hpem_grid_create(0, 1, a.ctypes.data_as(dptr), a.ctypes.data_as(dptr), a.ctypes.data_as(dptr), 1,
+                              a.ctypes.data_as(dptr), ctypes.byref(handle))
+    assert rc == -1 and b'n_angles' in lib.hpem_last_error()
+    rc = lib.hpem_grid_create(99, 4, a.ctypes.data_as(dptr), a.ctypes.data_as(dptr), a.ctypes.data_as(dptr), 1,
+                              a.ctypes.data_as(dptr), ctypes.byref(handle))
+    assert rc == -1 and b'device' in lib.hpem_last_error()
+    rc = lib.hpem_eval(None, 10, None, None, 133.322, 0, None)
+    assert rc == -1
+    assert lib.hpem_launch_count() >= 0
+
+
+def test_nonuniform_grid_uses_direct_kernel(cuda_device):
+    """A grid that is not i*h falls back to the direct kernel (hpem_grid_is_uniform == 0) and still matches the
+    restated reference evaluated on that grid."""
+    from hallthrusterpem_b200.engine import GridHandle
+    g = GridHandle(0, 91, np.array([1.0]))
+    assert g.uniform
+    g.close()
+    alpha = np.linspace(0, np.pi / 2, 91) ** 1.2 / (np.pi / 2) ** 0.2
+    g2 = GridHandle(0, 91, np.array([1.0]), alpha=alpha)
+    assert not g2.uniform
+    g2.close()
