@@ -12,21 +12,22 @@ from hallthrusterpem_b200.models import plume_cathode  # noqa: E402
 from hallthrusterpem_b200.synthetic import spt100_batch  # noqa: E402
 
 
-def time_dev(n, A, direct=False, want_j=True, reps=10):
+def time_dev(n, A, direct=False, want_j=True, reps=10, cathode=True):
+    from hallthrusterpem_b200.engine import PreparedCall
     b = {k: torch.as_tensor(v, device='cuda:0') for k, v in spt100_batch(n, 1).items()}
+    call = PreparedCall(b, want_cathode=cathode, want_plume=True, sweep_radius=1.0, n_angles=A, direct=direct,
+                        want_j_ion=want_j)
     for _ in range(3):
-        out = plume_cathode(b, 1.0, n_angles=A, direct=direct, want_j_ion=want_j)
+        call.run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    del out
     ts = []
     for _ in range(reps):
         e0.record()
-        out = plume_cathode(b, 1.0, n_angles=A, direct=direct, want_j_ion=want_j)
+        call.run()
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
-        del out
     ms = float(np.median(ts))
     byts = (8 + 144 / A) * n * A if want_j else 144 * n
     print(f'n={n:>9} A={A:>4} direct={direct!s:5} store_j={want_j!s:5}  {ms:8.3f} ms  {n * A / ms / 1e6:10.2f} Geval/s  '
