@@ -1,5 +1,6 @@
 // hpem_api.cu -- C ABI of libhpem (see include/hpem.h).  Host side: argument checking, grid handle,
 // kernel dispatch, and the host-buffer pipeline (H2D -> kernel -> D2H, chunked over samples).
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -75,7 +76,7 @@ struct hpem_grid {
     double2* d_w = nullptr;
     double* d_alpha = nullptr;
     double* d_radii = nullptr;
-    size_t smem_uniform = 0;
+    size_t smem_tma = 0, smem_stg = 0, smem_nostore = 0;  // dynamic shared memory of the K1u variants
     bool smem_ok = false;
     Workspace ws;
 };
@@ -121,19 +122,61 @@ void fill_params(const hpem_grid& g, const hpem_inputs& in, const hpem_outputs& 
     p.has_thrust = out.T_c != nullptr;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+
+// Tensor map of j_ion viewed as (rows = samples, cols = angles), box = 32 samples x 16 angles, 128B swizzle.
+int make_j_map(double* j_ion, int n_angles, long long n_rows, CUtensorMap* map) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(HPEM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t dims[2] = {(cuuint64_t)n_angles, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)n_angles * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)hpem::kChunk, 32u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, j_ion, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HPEM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return HPEM_OK;
+}
+
 int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store_j, uint32_t flags, cudaStream_t st) {
     using namespace hpem;
     if (p.n <= 0) return HPEM_OK;
     const bool use_uniform = g.uniform && g.n_radii == 1 && g.smem_ok && !(flags & HPEM_FLAG_FORCE_DIRECT);
     if (use_uniform || !plume) {
         const unsigned blocks = (unsigned)((p.n + kThreadsU - 1) / kThreadsU);
-        const size_t smem = plume ? g.smem_uniform : 0;
-        if (!plume)
-            eval_uniform_kernel<false, false><<<blocks, kThreadsU, 0, st>>>(p);
-        else if (store_j)
-            eval_uniform_kernel<true, true><<<blocks, kThreadsU, smem, st>>>(p);
-        else
-            eval_uniform_kernel<true, false><<<blocks, kThreadsU, smem, st>>>(p);
+        CUtensorMap map;
+        std::memset(&map, 0, sizeof(map));
+        if (!plume) {
+            eval_uniform_kernel<false, false, false><<<blocks, kThreadsU, 0, st>>>(p, map);
+        } else if (!store_j) {
+            eval_uniform_kernel<true, false, false><<<blocks, kThreadsU, g.smem_nostore, st>>>(p, map);
+        } else {
+            // TMA tensor stores need 16-byte aligned rows: even angle count and a 16-byte aligned base
+            const bool tma_ok = (g.n_angles % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.j_ion) & 15u) == 0) &&
+                                !(flags & HPEM_FLAG_NO_TMA);
+            if (tma_ok) {
+                int rc = make_j_map(p.j_ion, g.n_angles, p.n, &map);
+                if (rc != HPEM_OK) return rc;
+                eval_uniform_kernel<true, true, true><<<blocks, kThreadsU, g.smem_tma, st>>>(p, map);
+            } else {
+                eval_uniform_kernel<true, true, false><<<blocks, kThreadsU, g.smem_stg, st>>>(p, map);
+            }
+        }
     } else {
         const unsigned blocks = (unsigned)((p.n + kWarpsD - 1) / kWarpsD);
         eval_direct_kernel<true><<<blocks, kThreadsD, 0, st>>>(p);
@@ -224,11 +267,15 @@ int hpem_grid_create(int device, int n_angles, const double* alpha, const double
     HPEM_CUDA_G(cudaMemcpy(g->d_radii, radii, n_radii * sizeof(double), cudaMemcpyHostToDevice));
 #undef HPEM_CUDA_G
 
-    g->smem_uniform = size_t(g->n_angles_pad) * sizeof(double2) + size_t(hpem::kWarpsU) * 32 * hpem::kTilePitch * sizeof(double);
-    g->smem_ok = g->smem_uniform <= 200 * 1024;
+    const size_t wbytes = size_t(g->n_angles_pad) * sizeof(double2) + 1024;  // + slack for the 1024-byte alignment
+    g->smem_nostore = wbytes;
+    g->smem_stg = wbytes + size_t(hpem::kWarpsU) * 32 * hpem::kTilePitch * sizeof(double);
+    g->smem_tma = wbytes + size_t(hpem::kWarpsU) * hpem::kTmaBuffers * hpem::kTmaTileBytes;
+    g->smem_ok = std::max(g->smem_stg, g->smem_tma) <= 200 * 1024;
     if (g->smem_ok) {
-        int rc = set_smem(hpem::eval_uniform_kernel<true, true>, g->smem_uniform);
-        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, false>, g->smem_uniform);
+        int rc = set_smem(hpem::eval_uniform_kernel<true, true, true>, g->smem_tma);
+        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, true, false>, g->smem_stg);
+        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, false, false>, g->smem_nostore);
         if (rc != HPEM_OK) return cleanup(rc);
     }
     *out = g;

@@ -15,7 +15,10 @@
 // Reference lines reproduced: plume.py:95-127,136-140 (per angle / per sample epilogue),
 // cathode.py:26-37 and plume.py:40-85 via hpem_device.cuh.
 #pragma once
+#include <cuda.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 #include "hpem_device.cuh"
 
@@ -63,17 +66,72 @@ __device__ __forceinline__ double load_in(const EvalParams& p, int k, long long 
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA helpers (cp.async.bulk.tensor store, shared::cta -> global)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0),
+                 "r"(c1), "r"(smem_src)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // K1u: thread per sample, uniform grid, R == 1
 // ---------------------------------------------------------------------------------------------
-template <bool WANT_PLUME, bool STORE_J>
-__global__ void __launch_bounds__(kThreadsU) eval_uniform_kernel(const EvalParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* wsm = reinterpret_cast<double2*>(smem_raw);
-    double* tiles = reinterpret_cast<double*>(smem_raw + size_t(p.n_angles_pad) * sizeof(double2));
+constexpr int kTmaTileBytes = 32 * kChunk * 8;  // 32 samples x 16 angles, dense 128-byte rows (SWIZZLE_128B)
+constexpr int kTmaBuffers = 2;
+
+struct BeamState {  // per-thread recurrence state of one Gaussian beam
+    double ec, rc, gc;     // chunk-start profile value, chunk-start ratio, chunk-to-chunk factor
+    double q, qk, hh;      // per-sample constants exp(-2x), exp(-2Kx), exp(-2K^2 x)
+    double x, amp;
+};
+
+__device__ __forceinline__ void beam_init(BeamState& b, double h, double a, double amp) {
+    const double t = h / a;
+    b.x = t * t;                           // profile(i) = exp(-x i^2)
+    b.amp = amp;
+    b.q = exp(-2.0 * b.x);
+    b.qk = exp(-(2.0 * kChunk) * b.x);
+    b.hh = exp(-(2.0 * kChunk * kChunk) * b.x);
+    b.rc = exp(-b.x);
+    b.gc = exp(-double(kChunk * kChunk) * b.x);
+    b.ec = 1.0;
+}
+__device__ __forceinline__ void beam_restart(BeamState& b, int i0) {  // exact values at angle index i0
+    const double di = double(i0);
+    b.ec = exp(-b.x * (di * di));
+    b.rc = exp(-b.x * (2.0 * di + 1.0));
+    b.gc = exp(-b.x * (2.0 * kChunk * di + double(kChunk * kChunk)));
+}
+__device__ __forceinline__ void beam_next_chunk(BeamState& b) {
+    b.ec *= b.gc;
+    b.gc *= b.hh;
+    b.rc *= b.qk;
+}
+
+template <bool WANT_PLUME, bool STORE_J, bool USE_TMA>
+__global__ void __launch_bounds__(kThreadsU) eval_uniform_kernel(const EvalParams p,
+                                                                 const __grid_constant__ CUtensorMap jmap) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // layout: [staging tiles (1024-byte aligned for the 128B TMA swizzle)] [fused weights]
+    unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int kStageBytesPerWarp = USE_TMA ? kTmaBuffers * kTmaTileBytes : 32 * kTilePitch * 8;
+    constexpr int kStageBytes = STORE_J ? kWarpsU * kStageBytesPerWarp : 0;
+    double2* wsm = reinterpret_cast<double2*>(smem_al + kStageBytes);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    double* tile = tiles + warp * (32 * kTilePitch);
+    unsigned char* stage = smem_al + warp * kStageBytesPerWarp;
 
     if (WANT_PLUME) {
         for (int i = threadIdx.x; i < p.n_angles_pad; i += kThreadsU) wsm[i] = p.w[i];
@@ -99,22 +157,15 @@ __global__ void __launch_bounds__(kThreadsU) eval_uniform_kernel(const EvalParam
                                                load_in(p, IN_c3, s), load_in(p, IN_c4, s), load_in(p, IN_c5, s), p.torr);
     double j_cex, base;
     cex_terms(k.density, load_in(p, IN_sigma, s), load_in(p, IN_I_B0, s), p.radius0, j_cex, base);
-    const double amp1 = __dmul_rn(base, k.amp1);  // (base_density * A1), plume.py:99
-    const double amp2 = __dmul_rn(base, k.amp2);  // (base_density * A2), plume.py:100
 
-    // x_b = (h / a_b)^2 ; profile_b(i) = exp(-x_b i^2)
-    const double t1 = p.h / k.a1, t2 = p.h / k.a2;
-    const double x1 = t1 * t1, x2 = t2 * t2;
-    // recurrence constants: r(i) = exp(-x(2i+1)), q = exp(-2x); chunk level: R(c+1) = R(c)*QK,
-    // E(c+1) = E(c)*G(c), G(c+1) = G(c)*H
-    const double q1 = exp(-2.0 * x1), q2 = exp(-2.0 * x2);
-    const double qk1 = exp(-(2.0 * kChunk) * x1), qk2 = exp(-(2.0 * kChunk) * x2);
-    const double hh1 = exp(-(2.0 * kChunk * kChunk) * x1), hh2 = exp(-(2.0 * kChunk * kChunk) * x2);
-    double rc1 = exp(-x1), rc2 = exp(-x2);
-    double gc1 = exp(-double(kChunk * kChunk) * x1), gc2 = exp(-double(kChunk * kChunk) * x2);
-    double ec1 = 1.0, ec2 = 1.0;
+    BeamState b1, b2;
+    beam_init(b1, p.h, k.a1, __dmul_rn(base, k.amp1));   // (base_density * A1), plume.py:99
+    beam_init(b2, p.h, k.a2, __dmul_rn(base, k.amp2));   // (base_density * A2), plume.py:100
 
     const bool known_invalid = (k.a1 <= 0.0);  // plume.py:105 first term
+    // With non-negative beam amplitudes and a positive CEX floor every j_ion is > 0 (or NaN), so the per-angle
+    // `j_ion <= 0` test of plume.py:105 cannot fire; only warps holding an exceptional sample run the checked loop.
+    const bool needs_check = known_invalid || !(b1.amp >= 0.0 && b2.amp >= 0.0 && j_cex > 0.0);
     bool bad = false;
     double num = 0.0, den = 0.0;
 
@@ -123,64 +174,98 @@ __global__ void __launch_bounds__(kThreadsU) eval_uniform_kernel(const EvalParam
     const int rows_valid = (int)min((long long)32, p.n - warp_s0);
     const int col = lane & (kChunk - 1);
     const int rsub = lane >> 4;
-    double* gp = STORE_J ? p.j_ion + (warp_s0 + rsub) * (long long)A + col : nullptr;
-    double* my_tile_row = tile + lane * kTilePitch;
 
-    for (int c = 0; c < n_chunks; ++c) {
-        const int i0 = c * kChunk;
-        if (c != 0 && (c % kRestartChunks) == 0) {  // exact restart bounds the recurrence error for large A
-            const double di = double(i0);
-            ec1 = exp(-x1 * (di * di));
-            ec2 = exp(-x2 * (di * di));
-            rc1 = exp(-x1 * (2.0 * di + 1.0));
-            rc2 = exp(-x2 * (2.0 * di + 1.0));
-            gc1 = exp(-x1 * (2.0 * kChunk * di + double(kChunk * kChunk)));
-            gc2 = exp(-x2 * (2.0 * kChunk * di + double(kChunk * kChunk)));
-        }
-        double e1 = amp1 * ec1, e2 = amp2 * ec2;
-        double r1 = rc1, r2 = rc2;
-        const int kcount = min(kChunk, A - i0);
-        if (kcount == kChunk) {
-#pragma unroll
-            for (int kk = 0; kk < kChunk; ++kk) {
-                const double2 w = wsm[i0 + kk];
-                const double sum = e1 + e2;        // j_beam + j_scat
-                const double j = sum + j_cex;      // plume.py:102
+    auto chunk_loop = [&](auto checked_tag) {
+        constexpr bool CHECKED = decltype(checked_tag)::value;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int i0 = c * kChunk;
+            if (c != 0 && (c % kRestartChunks) == 0) {  // exact restart bounds the recurrence error for large A
+                beam_restart(b1, i0);
+                beam_restart(b2, i0);
+            }
+            double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec;
+            double r1 = b1.rc, r2 = b2.rc;
+            const int kcount = min(kChunk, A - i0);
+            unsigned char* my_row = USE_TMA ? stage + (c & 1) * kTmaTileBytes + lane * (kChunk * 8)
+                                            : stage + lane * (kTilePitch * 8);
+            auto step = [&](double2 w, double& jout) {
+                const double sum = e1 + e2;    // j_beam + j_scat
+                const double j = sum + j_cex;  // plume.py:102
                 den = fma(w.x, sum, den);
                 num = fma(w.y, sum, num);
-                bad |= (j <= 0.0);
-                if (STORE_J) my_tile_row[kk] = known_invalid ? kInvalidFill : j;
-                e1 *= r1; r1 *= q1;
-                e2 *= r2; r2 *= q2;
-            }
-        } else {
-            for (int kk = 0; kk < kcount; ++kk) {
-                const double2 w = wsm[i0 + kk];
-                const double sum = e1 + e2;
-                const double j = sum + j_cex;
-                den = fma(w.x, sum, den);
-                num = fma(w.y, sum, num);
-                bad |= (j <= 0.0);
-                if (STORE_J) my_tile_row[kk] = known_invalid ? kInvalidFill : j;
-                e1 *= r1; r1 *= q1;
-                e2 *= r2; r2 *= q2;
-            }
-        }
-        ec1 *= gc1; gc1 *= hh1; rc1 *= qk1;
-        ec2 *= gc2; gc2 *= hh2; rc2 *= qk2;
-
-        if (STORE_J) {
-            __syncwarp();
-            const double* trow = tile + rsub * kTilePitch + col;
-            double* g = gp + i0;
-            const bool col_ok = col < kcount;
+                if (CHECKED) {
+                    bad |= (j <= 0.0);
+                    jout = known_invalid ? kInvalidFill : j;
+                } else {
+                    jout = j;
+                }
+                e1 *= r1; r1 *= b1.q;
+                e2 *= r2; r2 *= b2.q;
+            };
+            if (kcount == kChunk) {
 #pragma unroll
-            for (int rr = 0; rr < 16; ++rr) {
-                if (col_ok && (2 * rr + rsub) < rows_valid) __stcs(g, trow[2 * rr * kTilePitch]);
-                g += 2 * (long long)A;
+                for (int kk = 0; kk < kChunk; kk += 2) {
+                    double ja, jb;
+                    step(wsm[i0 + kk], ja);
+                    step(wsm[i0 + kk + 1], jb);
+                    if (STORE_J) {
+                        if (USE_TMA) {
+                            *reinterpret_cast<double2*>(my_row + ((((kk >> 1) ^ (lane & 7))) << 4)) = make_double2(ja, jb);
+                        } else {
+                            reinterpret_cast<double*>(my_row)[kk] = ja;
+                            reinterpret_cast<double*>(my_row)[kk + 1] = jb;
+                        }
+                    }
+                }
+            } else {
+                for (int kk = 0; kk < kcount; ++kk) {
+                    double ja;
+                    step(wsm[i0 + kk], ja);
+                    if (STORE_J) {
+                        if (USE_TMA)
+                            *reinterpret_cast<double*>(my_row + ((((kk >> 1) ^ (lane & 7))) << 4) + ((kk & 1) << 3)) = ja;
+                        else
+                            reinterpret_cast<double*>(my_row)[kk] = ja;
+                    }
+                }
             }
-            __syncwarp();
+            beam_next_chunk(b1);
+            beam_next_chunk(b2);
+
+            if (STORE_J) {
+                if (USE_TMA) {
+                    // one 32x16 box per warp and chunk; rows >= n and columns >= A are clipped by the tensor map
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&jmap, smem_u32(stage + (c & 1) * kTmaTileBytes), i0, (int)warp_s0);
+                        tma_wait_read<kTmaBuffers - 1>();   // the other buffer is free again
+                    }
+                    __syncwarp();
+                } else {
+                    __syncwarp();
+                    const double* trow = reinterpret_cast<const double*>(stage) + rsub * kTilePitch + col;
+                    double* g = p.j_ion + (warp_s0 + rsub) * (long long)A + col + i0;
+                    const bool col_ok = col < kcount;
+#pragma unroll
+                    for (int rr = 0; rr < 16; ++rr) {
+                        if (col_ok && (2 * rr + rsub) < rows_valid) __stcs(g, trow[2 * rr * kTilePitch]);
+                        g += 2 * (long long)A;
+                    }
+                    __syncwarp();
+                }
+            }
         }
+    };
+    if (__any_sync(0xffffffffu, needs_check))
+        chunk_loop(std::true_type{});
+    else
+        chunk_loop(std::false_type{});
+
+    if (STORE_J && USE_TMA) {
+        if (lane == 0) tma_wait_all();
+        fence_async_all();
+        __syncwarp();
     }
 
     // per-sample epilogue: plume.py:124-127,137 (NOT masked by `invalid`)
@@ -194,7 +279,7 @@ __global__ void __launch_bounds__(kThreadsU) eval_uniform_kernel(const EvalParam
         if (p.invalid) p.invalid[s] = invalid ? 1 : 0;
         if (STORE_J && bad && !known_invalid) {
             // rare: a non-positive j_ion found after earlier chunks were already written -> overwrite the
-            // row (plume.py:106).  The __syncwarp() after the last store-out orders those stores first.
+            // row (plume.py:106).  All of this warp's earlier stores are complete and ordered before this point.
             double* row = p.j_ion + s * (long long)A;
             for (int i = 0; i < A; ++i) row[i] = kInvalidFill;
         }

@@ -85,6 +85,8 @@ typedef struct hpem_outputs {
 /* flags for hpem_eval / hpem_eval_host */
 #define HPEM_FLAG_FORCE_DIRECT 1u /* use the direct kernel (one exp per beam per angle, the reference's  \
                                      operation order) even when the angle grid is uniform */
+#define HPEM_FLAG_NO_TMA 2u       /* recurrence kernel: stage j_ion through plain st.global instead of TMA tensor   \
+                                     stores (always the case for odd angle counts: rows are not 16-byte aligned) */
 
 typedef struct hpem_grid hpem_grid; /* opaque */
 

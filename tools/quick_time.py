@@ -12,11 +12,11 @@ from hallthrusterpem_b200.models import plume_cathode  # noqa: E402
 from hallthrusterpem_b200.synthetic import spt100_batch  # noqa: E402
 
 
-def time_dev(n, A, direct=False, want_j=True, reps=10, cathode=True):
+def time_dev(n, A, direct=False, want_j=True, reps=10, cathode=True, no_tma=False):
     from hallthrusterpem_b200.engine import PreparedCall
     b = {k: torch.as_tensor(v, device='cuda:0') for k, v in spt100_batch(n, 1).items()}
     call = PreparedCall(b, want_cathode=cathode, want_plume=True, sweep_radius=1.0, n_angles=A, direct=direct,
-                        want_j_ion=want_j)
+                        want_j_ion=want_j, no_tma=no_tma)
     for _ in range(3):
         call.run()
     torch.cuda.synchronize()
@@ -30,7 +30,7 @@ def time_dev(n, A, direct=False, want_j=True, reps=10, cathode=True):
         ts.append(e0.elapsed_time(e1))
     ms = float(np.median(ts))
     byts = (8 + 144 / A) * n * A if want_j else 144 * n
-    print(f'n={n:>9} A={A:>4} direct={direct!s:5} store_j={want_j!s:5}  {ms:8.3f} ms  {n * A / ms / 1e6:10.2f} Geval/s  '
+    print(f'n={n:>9} A={A:>4} direct={direct!s:5} no_tma={no_tma!s:5} store_j={want_j!s:5}  {ms:8.3f} ms  {n * A / ms / 1e6:10.2f} Geval/s  '
           f'{byts / ms / 1e6:8.1f} GB/s (algorithmic)  min {min(ts):.3f} ms', flush=True)
 
 
@@ -53,6 +53,7 @@ def time_host(n, A, reps=3):
 if __name__ == '__main__':
     for n, A in ((1_000_000, 200), (1_000_000, 91), (4_000_000, 256), (1_000_000, 512)):
         time_dev(n, A)
+        time_dev(n, A, no_tma=True)
         time_dev(n, A, want_j=False)
     time_dev(1_000_000, 200, direct=True)
     time_host(1_000_000, 200)
