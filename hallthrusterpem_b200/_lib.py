@@ -28,6 +28,8 @@ PLUME_INPUTS = ('P_b',) + INPUT_NAMES[6:14]
 HPEM_OK = 0
 FLAG_FORCE_DIRECT = 1
 FLAG_NO_TMA = 2
+FLAG_LANES1 = 4
+FLAG_LANES4 = 8
 
 EXPORTED_SYMBOLS = (
     'hpem_abi_version', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',

@@ -77,6 +77,7 @@ struct hpem_grid {
     double* d_alpha = nullptr;
     double* d_radii = nullptr;
     size_t smem_tma = 0, smem_stg = 0, smem_nostore = 0;  // dynamic shared memory of the K1u variants
+    size_t smem_v_store = 0, smem_v_nostore = 0;          // ... and of K1v
     bool smem_ok = false;
     Workspace ws;
 };
@@ -120,6 +121,7 @@ void fill_params(const hpem_grid& g, const hpem_inputs& in, const hpem_outputs& 
     p.h = g.h;
     p.radius0 = g.radius0;
     p.has_thrust = out.T_c != nullptr;
+    p.bulk_ok = false;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time dependency on libcuda)
@@ -139,16 +141,18 @@ EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// Tensor map of j_ion viewed as (rows = samples, cols = angles), box = 32 samples x 16 angles, 128B swizzle.
-int make_j_map(double* j_ion, int n_angles, long long n_rows, CUtensorMap* map) {
+// Tensor map of j_ion viewed as (rows = samples, cols = angles); box = box_rows samples x box_cols angles.
+int make_j_map(double* j_ion, int n_angles, long long n_rows, int box_cols, int box_rows, bool swizzle128,
+               CUtensorMap* map) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(HPEM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     const cuuint64_t dims[2] = {(cuuint64_t)n_angles, (cuuint64_t)n_rows};
     const cuuint64_t strides[1] = {(cuuint64_t)n_angles * sizeof(double)};
-    const cuuint32_t box[2] = {(cuuint32_t)hpem::kChunk, 32u};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1u, 1u};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, j_ion, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HPEM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return HPEM_OK;
 }
@@ -161,21 +165,32 @@ int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store
         const unsigned blocks = (unsigned)((p.n + kThreadsU - 1) / kThreadsU);
         CUtensorMap map;
         std::memset(&map, 0, sizeof(map));
+        // TMA tensor stores need 16-byte aligned rows: even angle count and a 16-byte aligned base
+        const bool tma_ok = store_j && (g.n_angles % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.j_ion) & 15u) == 0) &&
+                            !(flags & HPEM_FLAG_NO_TMA);
+        // default choice (measured on B200, tools/variant_sweep.py): TMA tensor stores need even A, and with them the
+        // one-lane sweep (K1u) is the faster kernel; for odd A the four-lane sweep with whole-row bulk stores (K1v) wins
+        const bool lanes1 = (flags & HPEM_FLAG_LANES1) ? true : (flags & HPEM_FLAG_LANES4) ? false : (g.n_angles % 2 == 0);
         if (!plume) {
             eval_uniform_kernel<false, false, false><<<blocks, kThreadsU, 0, st>>>(p, map);
-        } else if (!store_j) {
-            eval_uniform_kernel<true, false, false><<<blocks, kThreadsU, g.smem_nostore, st>>>(p, map);
-        } else {
-            // TMA tensor stores need 16-byte aligned rows: even angle count and a 16-byte aligned base
-            const bool tma_ok = (g.n_angles % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.j_ion) & 15u) == 0) &&
-                                !(flags & HPEM_FLAG_NO_TMA);
-            if (tma_ok) {
-                int rc = make_j_map(p.j_ion, g.n_angles, p.n, &map);
+        } else if (lanes1) {   // K1u: one lane per sample for the angle sweep as well (128-byte row pieces)
+            if (!store_j) {
+                eval_uniform_kernel<true, false, false><<<blocks, kThreadsU, g.smem_nostore, st>>>(p, map);
+            } else if (tma_ok) {
+                int rc = make_j_map(p.j_ion, g.n_angles, p.n, kChunk, 32, true, &map);
                 if (rc != HPEM_OK) return rc;
                 eval_uniform_kernel<true, true, true><<<blocks, kThreadsU, g.smem_tma, st>>>(p, map);
             } else {
                 eval_uniform_kernel<true, true, false><<<blocks, kThreadsU, g.smem_stg, st>>>(p, map);
             }
+        } else {               // K1v: four lanes per sample in the sweep, whole rows per bulk store
+            const unsigned vblocks = (unsigned)((p.n + kThreadsV - 1) / kThreadsV);
+            hpem::EvalParams pv = p;
+            pv.bulk_ok = store_j && ((reinterpret_cast<uintptr_t>(p.j_ion) & 15u) == 0) && !(flags & HPEM_FLAG_NO_TMA);
+            if (!store_j)
+                eval_lanes4_kernel<false><<<vblocks, kThreadsV, g.smem_v_nostore, st>>>(pv);
+            else
+                eval_lanes4_kernel<true><<<vblocks, kThreadsV, g.smem_v_store, st>>>(pv);
         }
     } else {
         const unsigned blocks = (unsigned)((p.n + kWarpsD - 1) / kWarpsD);
@@ -234,7 +249,7 @@ int hpem_grid_create(int device, int n_angles, const double* alpha, const double
     if (!g) return fail(HPEM_ERR_CUDA, "out of host memory");
     g->device = device;
     g->n_angles = n_angles;
-    g->n_angles_pad = (n_angles + hpem::kChunk - 1) / hpem::kChunk * hpem::kChunk;
+    g->n_angles_pad = (n_angles + hpem::kAnglePad - 1) / hpem::kAnglePad * hpem::kAnglePad;
     g->n_radii = n_radii;
     g->radius0 = radii[0];
     g->h = alpha[1];
@@ -271,11 +286,16 @@ int hpem_grid_create(int device, int n_angles, const double* alpha, const double
     g->smem_nostore = wbytes;
     g->smem_stg = wbytes + size_t(hpem::kWarpsU) * 32 * hpem::kTilePitch * sizeof(double);
     g->smem_tma = wbytes + size_t(hpem::kWarpsU) * hpem::kTmaBuffers * hpem::kTmaTileBytes;
-    g->smem_ok = std::max(g->smem_stg, g->smem_tma) <= 200 * 1024;
+    const size_t xbytes = size_t(hpem::kWarpsV) * 32 * hpem::kXchPitch * sizeof(double);
+    g->smem_v_nostore = wbytes + xbytes;
+    g->smem_v_store = wbytes + xbytes + size_t(hpem::kWarpsV) * hpem::k1v_tile_bytes(n_angles);
+    g->smem_ok = std::max(std::max(g->smem_stg, g->smem_tma), g->smem_v_store) <= 200 * 1024;
     if (g->smem_ok) {
         int rc = set_smem(hpem::eval_uniform_kernel<true, true, true>, g->smem_tma);
         if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, true, false>, g->smem_stg);
         if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, false, false>, g->smem_nostore);
+        if (rc == HPEM_OK) rc = set_smem(hpem::eval_lanes4_kernel<true>, g->smem_v_store);
+        if (rc == HPEM_OK) rc = set_smem(hpem::eval_lanes4_kernel<false>, g->smem_v_nostore);
         if (rc != HPEM_OK) return cleanup(rc);
     }
     *out = g;
@@ -350,7 +370,7 @@ int hpem_eval_host(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_ou
     const int64_t cap_elems = ((int64_t)16 << 30) / 8;
     const int64_t batch = out->j_ion ? std::max<int64_t>(1, std::min<int64_t>(n, cap_elems / row_elems)) : n;
     // D2H chunks of ~32 MiB so the copy engine starts as soon as the first rows exist
-    const int64_t chunk = out->j_ion ? std::max<int64_t>(1024, ((int64_t)32 << 20) / (row_elems * 8)) : batch;
+    const int64_t chunk = out->j_ion ? (std::max<int64_t>(1024, ((int64_t)32 << 20) / (row_elems * 8)) + 63) / 64 * 64 : batch;
 
     for (int64_t b0 = 0; b0 < n; b0 += batch) {
         const int64_t nb = std::min(batch, n - b0);

@@ -52,12 +52,16 @@ struct EvalParams {
     double h;                // uniform step alpha[1] (uniform kernel only)
     double radius0;          // radii[0]
     bool has_thrust;         // input T supplied
+    bool bulk_ok;            // j_ion base is 16-byte aligned and bulk (TMA) stores are allowed
 };
 
 constexpr int kChunk = 16;          // angles per staged tile / inner recurrence length
 constexpr int kRestartChunks = 16;  // exact exp() restart every kRestartChunks*kChunk angles
 constexpr int kTilePitch = kChunk + 1;
-constexpr int kThreadsU = 128;
+#ifndef HPEM_THREADS_U
+#define HPEM_THREADS_U 128
+#endif
+constexpr int kThreadsU = HPEM_THREADS_U;
 constexpr int kWarpsU = kThreadsU / 32;
 constexpr double kInvalidFill = 1e-20;  // plume.py:106
 
@@ -88,7 +92,10 @@ __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.as
 // K1u: thread per sample, uniform grid, R == 1
 // ---------------------------------------------------------------------------------------------
 constexpr int kTmaTileBytes = 32 * kChunk * 8;  // 32 samples x 16 angles, dense 128-byte rows (SWIZZLE_128B)
-constexpr int kTmaBuffers = 2;
+#ifndef HPEM_TMA_BUFFERS
+#define HPEM_TMA_BUFFERS 2
+#endif
+constexpr int kTmaBuffers = HPEM_TMA_BUFFERS;
 
 struct BeamState {  // per-thread recurrence state of one Gaussian beam
     double ec, rc, gc;     // chunk-start profile value, chunk-start ratio, chunk-to-chunk factor
@@ -119,8 +126,11 @@ __device__ __forceinline__ void beam_next_chunk(BeamState& b) {
     b.rc *= b.qk;
 }
 
+#ifndef HPEM_MIN_BLOCKS_U
+#define HPEM_MIN_BLOCKS_U 6
+#endif
 template <bool WANT_PLUME, bool STORE_J, bool USE_TMA>
-__global__ void __launch_bounds__(kThreadsU) eval_uniform_kernel(const EvalParams p,
+__global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_kernel(const EvalParams p,
                                                                  const __grid_constant__ CUtensorMap jmap) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // layout: [staging tiles (1024-byte aligned for the 128B TMA swizzle)] [fused weights]
@@ -144,19 +154,25 @@ __global__ void __launch_bounds__(kThreadsU) eval_uniform_kernel(const EvalParam
     const long long warp_s0 = s_raw - lane;
     if (warp_s0 >= p.n) return;  // whole warp out of range (after the only __syncthreads)
 
-    const double p_b = load_in(p, IN_P_b, s);
+    // all per-sample loads are issued up front (15 independent LDG.64 in flight per thread)
+    double x_in[kNumInputs];
+#pragma unroll
+    for (int q = 0; q < kNumInputs; ++q) {
+        const bool needed = (q == IN_P_b) || (q <= IN_P_T ? p.v_cc != nullptr : (q == IN_T ? p.t_c != nullptr : WANT_PLUME));
+        x_in[q] = needed ? load_in(p, q, s) : 0.0;
+    }
+    const double p_b = x_in[IN_P_b];
 
     if (p.v_cc) {
-        const double v = cathode_vcc(p_b, load_in(p, IN_V_a, s), load_in(p, IN_T_e, s), load_in(p, IN_V_vac, s),
-                                     load_in(p, IN_Pstar, s), load_in(p, IN_P_T, s), p.torr);
+        const double v = cathode_vcc(p_b, x_in[IN_V_a], x_in[IN_T_e], x_in[IN_V_vac], x_in[IN_Pstar], x_in[IN_P_T], p.torr);
         if (active) p.v_cc[s] = v;
     }
     if (!WANT_PLUME) return;
 
-    const SampleConsts k = plume_sample_consts(p_b, load_in(p, IN_c0, s), load_in(p, IN_c1, s), load_in(p, IN_c2, s),
-                                               load_in(p, IN_c3, s), load_in(p, IN_c4, s), load_in(p, IN_c5, s), p.torr);
+    const SampleConsts k = plume_sample_consts(p_b, x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3], x_in[IN_c4],
+                                               x_in[IN_c5], p.torr);
     double j_cex, base;
-    cex_terms(k.density, load_in(p, IN_sigma, s), load_in(p, IN_I_B0, s), p.radius0, j_cex, base);
+    cex_terms(k.density, x_in[IN_sigma], x_in[IN_I_B0], p.radius0, j_cex, base);
 
     BeamState b1, b2;
     beam_init(b1, p.h, k.a1, __dmul_rn(base, k.amp1));   // (base_density * A1), plume.py:99
@@ -186,7 +202,7 @@ __global__ void __launch_bounds__(kThreadsU) eval_uniform_kernel(const EvalParam
             double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec;
             double r1 = b1.rc, r2 = b2.rc;
             const int kcount = min(kChunk, A - i0);
-            unsigned char* my_row = USE_TMA ? stage + (c & 1) * kTmaTileBytes + lane * (kChunk * 8)
+            unsigned char* my_row = USE_TMA ? stage + (c % kTmaBuffers) * kTmaTileBytes + lane * (kChunk * 8)
                                             : stage + lane * (kTilePitch * 8);
             auto step = [&](double2 w, double& jout) {
                 const double sum = e1 + e2;    // j_beam + j_scat
@@ -238,7 +254,7 @@ __global__ void __launch_bounds__(kThreadsU) eval_uniform_kernel(const EvalParam
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&jmap, smem_u32(stage + (c & 1) * kTmaTileBytes), i0, (int)warp_s0);
+                        tma_store_2d(&jmap, smem_u32(stage + (c % kTmaBuffers) * kTmaTileBytes), i0, (int)warp_s0);
                         tma_wait_read<kTmaBuffers - 1>();   // the other buffer is free again
                     }
                     __syncwarp();
@@ -262,9 +278,15 @@ __global__ void __launch_bounds__(kThreadsU) eval_uniform_kernel(const EvalParam
     else
         chunk_loop(std::false_type{});
 
+    // rare: a non-positive j_ion found after earlier chunks were already written -> the row is overwritten below
+    const bool late_fix = STORE_J && __any_sync(0xffffffffu, bad && !known_invalid);
     if (STORE_J && USE_TMA) {
-        if (lane == 0) tma_wait_all();
-        fence_async_all();
+        if (late_fix) {            // order the TMA (async proxy) writes before the generic-proxy rewrite
+            if (lane == 0) tma_wait_all();
+            fence_async_all();
+        } else if (lane == 0) {
+            tma_wait_read<0>();    // the staging tiles must outlive the TMA reads
+        }
         __syncwarp();
     }
 
@@ -275,11 +297,312 @@ __global__ void __launch_bounds__(kThreadsU) eval_uniform_kernel(const EvalParam
     if (active) {
         if (p.div_angle) p.div_angle[s] = acos(cd);
         if (p.cos_div) p.cos_div[s] = cd;
-        if (p.t_c) p.t_c[s] = __dmul_rn(load_in(p, IN_T, s), cd);
+        if (p.t_c) p.t_c[s] = __dmul_rn(x_in[IN_T], cd);
         if (p.invalid) p.invalid[s] = invalid ? 1 : 0;
         if (STORE_J && bad && !known_invalid) {
-            // rare: a non-positive j_ion found after earlier chunks were already written -> overwrite the
-            // row (plume.py:106).  All of this warp's earlier stores are complete and ordered before this point.
+            // plume.py:106.  All of this warp's earlier stores are complete and ordered before this point.
+            double* row = p.j_ion + s * (long long)A;
+            for (int i = 0; i < A; ++i) row[i] = kInvalidFill;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1v: thread per sample for the per-sample work, FOUR lanes per sample for the angle sweep,
+//      whole rows staged in shared memory and written with ONE bulk (TMA) copy per 8 samples
+// ---------------------------------------------------------------------------------------------
+// HBM write efficiency depends on how many contiguous bytes reach L2 together: 128-byte row pieces (K1u's
+// 32 samples x 16 angles box) stream at ~5.6 TB/s on B200, 512-byte pieces at ~7.2 TB/s, >= 1 KB at ~7.4 TB/s
+// (tools/store_pattern.cu).  j_ion rows of consecutive samples are adjacent in memory, so K1v lets a group of
+// 8 samples sweep ALL angles into a dense shared-memory tile (8 x A doubles) and ships the tile as one contiguous
+// 8*A*8-byte cp.async.bulk store (works for odd A too: the group start is always 16-byte aligned).
+// Angle counts whose tile would exceed 16 KB are processed in panels of 256 angles (2 KB row pieces).
+// The sweep uses 4 lanes per sample, lane q taking angles i = q (mod 4) with a stride-4 Gaussian recurrence.  Per warp:
+//   phase 1  lane t <-> sample s0+t : loads, cathode, A1/A2, CEX terms, the 16 exps the recurrences start from
+//   phase 2  4 groups of 8 samples, lane (r = lane/4, q = lane%4): sweep + quadrature partial sums + tile + store
+//   phase 3  lane t <-> sample s0+t : cos_div, arccos, T_c, invalid mask, rare late fix-up
+// Only __syncwarp() separates the phases (each warp owns its 32 samples and its shared-memory slices).
+constexpr int kL4 = 4;                        // lanes per sample in the sweep
+constexpr int kSteps4 = 16;                   // recurrence steps per chunk (chunk = 64 angles)
+constexpr int kCols4 = kL4 * kSteps4;
+constexpr int kRows4 = 32 / kL4;              // 8 samples per group
+#ifndef HPEM_PANEL_MAX
+#define HPEM_PANEL_MAX 256
+#endif
+constexpr int kPanelMax = HPEM_PANEL_MAX;                // angles per staged panel (tile = 8 x 256 x 8 B = 16 KB)
+constexpr int kRestartChunks4 = 8;            // exact restart every 512 angles
+constexpr int kAnglePad = kCols4;             // weights are zero-padded to a multiple of this
+// doubles per sample handed from phase 1 to phase 2: amp1 amp2 j_cex flags x1 x2 + 8 base exps per beam
+constexpr int kXch = 22;
+constexpr int kXchPitch = 23;                 // odd pitch: conflict-free column access
+
+__device__ __forceinline__ void bulk_store_1d(double* gdst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// exp(-x*m) for the multipliers the stride-4 recurrence is assembled from
+__device__ __forceinline__ void beam_base_exps(double x, double* o) {
+    o[0] = exp(-x);                                   // u
+    o[1] = exp(-8.0 * x);                             // ratio step in q        (2 L)
+    o[2] = exp(-16.0 * x);                            // ratio at i = 0         (L^2)
+    o[3] = exp(-32.0 * x);                            // q  : ratio growth      (2 L^2)
+    o[4] = exp(-128.0 * x);                           // chunk factor step in q (2 L K)
+    o[5] = exp(-512.0 * x);                           // qk : ratio growth per chunk (2 L^2 K)
+    o[6] = exp(-4096.0 * x);                          // chunk factor at i = 0  ((L K)^2)
+    o[7] = exp(-8192.0 * x);                          // hh : chunk factor growth (2 (L K)^2)
+}
+
+struct BeamLane {       // per-lane recurrence state of one beam, stride-4 sweep
+    double ec, rc, gc;  // chunk-start value / ratio / chunk-to-chunk factor
+    double q, qk, hh;
+    double x, amp;
+};
+// lane-specific start values for angle index q in {0,1,2,3} from the per-sample base exps (products of <= 4 factors)
+__device__ __forceinline__ void beam_lane_init(BeamLane& b, const double* xr, int q) {
+    const double u = xr[0], e8 = xr[1], e16 = xr[2], e128 = xr[4], e4096 = xr[6];
+    b.q = xr[3];
+    b.qk = xr[5];
+    b.hh = xr[7];
+    const double u2 = u * u, u4 = u2 * u2, u8 = u4 * u4;
+    const double e8_2 = e8 * e8, e128_2 = e128 * e128;
+    // exp(-x q^2), exp(-x (8 q + 16)), exp(-x (128 q + 4096))
+    b.ec = (q == 0) ? 1.0 : (q == 1) ? u : (q == 2) ? u4 : u8 * u;
+    b.rc = e16 * ((q == 0) ? 1.0 : (q == 1) ? e8 : (q == 2) ? e8_2 : e8_2 * e8);
+    b.gc = e4096 * ((q == 0) ? 1.0 : (q == 1) ? e128 : (q == 2) ? e128_2 : e128_2 * e128);
+}
+__device__ __forceinline__ void beam_lane_restart(BeamLane& b, int i0) {  // exact values at angle index i0
+    const double di = double(i0);
+    b.ec = exp(-b.x * (di * di));
+    b.rc = exp(-b.x * (2.0 * kL4 * di + double(kL4 * kL4)));
+    b.gc = exp(-b.x * (2.0 * kCols4 * di + double(kCols4 * kCols4)));
+}
+__device__ __forceinline__ void beam_lane_next(BeamLane& b) {
+    b.ec *= b.gc;
+    b.gc *= b.hh;
+    b.rc *= b.qk;
+}
+
+#ifndef HPEM_THREADS_V
+#define HPEM_THREADS_V 64
+#endif
+#ifndef HPEM_MIN_BLOCKS_V
+#define HPEM_MIN_BLOCKS_V 8
+#endif
+constexpr int kThreadsV = HPEM_THREADS_V;
+constexpr int kWarpsV = kThreadsV / 32;
+
+// shared memory of K1v: [tiles: kWarpsV x tile_bytes (16-byte aligned)] [exchange] [weights]
+__host__ __device__ inline int k1v_panel_cols(int n_angles) { return n_angles <= kPanelMax ? n_angles : kPanelMax; }
+__host__ __device__ inline size_t k1v_tile_bytes(int n_angles) { return size_t(kRows4) * k1v_panel_cols(n_angles) * 8; }
+
+template <bool STORE_J>
+__global__ void __launch_bounds__(kThreadsV, HPEM_MIN_BLOCKS_V) eval_lanes4_kernel(const EvalParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int A = p.n_angles;
+    const int panel_cols = k1v_panel_cols(A);
+    const int tile_bytes = STORE_J ? (int)k1v_tile_bytes(A) : 0;
+    double* xch_all = reinterpret_cast<double*>(smem_raw + kWarpsV * tile_bytes);
+    double2* wsm = reinterpret_cast<double2*>(xch_all + kWarpsV * 32 * kXchPitch);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    double* tile = reinterpret_cast<double*>(smem_raw + warp * tile_bytes);
+    double* xch = xch_all + warp * 32 * kXchPitch;
+
+    for (int i = threadIdx.x; i < p.n_angles_pad; i += kThreadsV) wsm[i] = p.w[i];
+    __syncthreads();
+
+    const long long s_raw = (long long)blockIdx.x * kThreadsV + threadIdx.x;
+    const bool active = s_raw < p.n;
+    const long long s = active ? s_raw : p.n - 1;  // inactive lanes shadow the last sample, never store
+    const long long warp_s0 = s_raw - lane;
+    if (warp_s0 >= p.n) return;
+
+    // ---------------- phase 1: one lane per sample ----------------
+    double thrust = 0.0;
+    bool known_invalid;
+    {
+        double x_in[kNumInputs];
+#pragma unroll
+        for (int q = 0; q < kNumInputs; ++q) {
+            const bool needed = (q == IN_P_b) || (q <= IN_P_T ? p.v_cc != nullptr : (q == IN_T ? p.t_c != nullptr : true));
+            x_in[q] = needed ? load_in(p, q, s) : 0.0;
+        }
+        thrust = x_in[IN_T];
+        if (p.v_cc) {
+            const double v = cathode_vcc(x_in[IN_P_b], x_in[IN_V_a], x_in[IN_T_e], x_in[IN_V_vac], x_in[IN_Pstar],
+                                         x_in[IN_P_T], p.torr);
+            if (active) p.v_cc[s] = v;
+        }
+        const SampleConsts k = plume_sample_consts(x_in[IN_P_b], x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3],
+                                                   x_in[IN_c4], x_in[IN_c5], p.torr);
+        double j_cex, base;
+        cex_terms(k.density, x_in[IN_sigma], x_in[IN_I_B0], p.radius0, j_cex, base);
+        const double amp1 = __dmul_rn(base, k.amp1);  // (base_density * A1), plume.py:99
+        const double amp2 = __dmul_rn(base, k.amp2);  // (base_density * A2), plume.py:100
+        const double t1 = p.h / k.a1, t2 = p.h / k.a2;
+        const double x1 = t1 * t1, x2 = t2 * t2;      // profile_b(i) = exp(-x_b i^2)
+        known_invalid = (k.a1 <= 0.0);                 // plume.py:105 first term
+        // non-negative amplitudes and a positive CEX floor => every j_ion > 0 (or NaN): no per-angle test needed
+        const bool needs_check = known_invalid || !(amp1 >= 0.0 && amp2 >= 0.0 && j_cex > 0.0);
+        double* xr = xch + lane * kXchPitch;
+        xr[0] = amp1;
+        xr[1] = amp2;
+        xr[2] = j_cex;
+        xr[3] = __longlong_as_double((long long)((known_invalid ? 1 : 0) | (needs_check ? 2 : 0)));
+        xr[4] = x1;
+        xr[5] = x2;
+        double ex[8];
+        beam_base_exps(x1, ex);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xr[6 + j] = ex[j];
+        beam_base_exps(x2, ex);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xr[14 + j] = ex[j];
+    }
+    __syncwarp();
+
+    // ---------------- phase 2: four lanes per sample ----------------
+    const int r = lane >> 2, q = lane & 3;
+    const int qbase = lane & ~3;
+    const int n_panels = (A + panel_cols - 1) / panel_cols;
+    const bool bulk_rows_ok = (n_panels == 1);                 // whole rows staged: contiguous 1-D bulk store
+    const bool bulk_panel_ok = (A % 2 == 0);                   // panel rows are 16-byte aligned only for even A
+#pragma unroll 1
+    for (int g = 0; g < kL4; ++g) {
+        const long long grow0 = warp_s0 + g * kRows4;
+        if (grow0 >= p.n) break;  // warp-uniform
+        double* xr = xch + (g * kRows4 + r) * kXchPitch;
+        BeamLane b1, b2;
+        b1.amp = xr[0];
+        b2.amp = xr[1];
+        const double j_cex = xr[2];
+        const int flags = (int)__double_as_longlong(xr[3]);
+        b1.x = xr[4];
+        b2.x = xr[5];
+        beam_lane_init(b1, xr + 6, q);
+        beam_lane_init(b2, xr + 14, q);
+        const bool fill_invalid = flags & 1;
+        const int rows_valid = (int)min((long long)kRows4, p.n - grow0);
+        double num = 0.0, den = 0.0;
+        bool bad = false;
+
+        auto sweep = [&](auto checked_tag) {
+            constexpr bool CHECKED = decltype(checked_tag)::value;
+            int chunk = 0;
+#pragma unroll 1
+            for (int pn = 0; pn < n_panels; ++pn) {
+                const int col0 = pn * panel_cols;                  // first angle of the panel (multiple of 64 or 0)
+                const int cols = min(panel_cols, A - col0);
+                if (STORE_J) {   // the previous bulk store must have finished READING the tile before it is refilled
+                    tma_wait_read<0>();
+                    __syncwarp();
+                }
+                double* my = tile + r * cols + q;
+                const int n_ch = (cols + kCols4 - 1) / kCols4;
+#pragma unroll 1
+                for (int c = 0; c < n_ch; ++c, ++chunk) {
+                    const int i0 = col0 + c * kCols4;
+                    if (chunk != 0 && (chunk % kRestartChunks4) == 0) {
+                        beam_lane_restart(b1, i0 + q);
+                        beam_lane_restart(b2, i0 + q);
+                    }
+                    double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec;
+                    double r1 = b1.rc, r2 = b2.rc;
+                    const double2* wp = wsm + i0 + q;
+                    double* mine = my + c * kCols4;
+                    const int lim = A - i0 - q;                    // step m is a real angle iff kL4*m < lim
+                    auto step = [&](int m) {
+                        const double2 w = wp[kL4 * m];             // zero beyond A (padding)
+                        const double sum = e1 + e2;                // j_beam + j_scat
+                        const double j = sum + j_cex;              // plume.py:102
+                        den = fma(w.x, sum, den);
+                        num = fma(w.y, sum, num);
+                        const bool real = kL4 * m < lim;
+                        if (CHECKED) bad |= (j <= 0.0) && real;
+                        if (STORE_J && real) mine[kL4 * m] = (CHECKED && fill_invalid) ? kInvalidFill : j;
+                        e1 *= r1; r1 *= b1.q;
+                        e2 *= r2; r2 *= b2.q;
+                    };
+                    if (lim >= kCols4) {
+#pragma unroll
+                        for (int m = 0; m < kSteps4; ++m) {
+                            const double2 w = wp[kL4 * m];
+                            const double sum = e1 + e2;
+                            const double j = sum + j_cex;
+                            den = fma(w.x, sum, den);
+                            num = fma(w.y, sum, num);
+                            if (CHECKED) bad |= (j <= 0.0);
+                            if (STORE_J) mine[kL4 * m] = (CHECKED && fill_invalid) ? kInvalidFill : j;
+                            e1 *= r1; r1 *= b1.q;
+                            e2 *= r2; r2 *= b2.q;
+                        }
+                    } else {
+                        const int m_end = min(kSteps4, (A - i0 + kL4 - 1) / kL4);   // warp-uniform
+                        for (int m = 0; m < m_end; ++m) step(m);
+                    }
+                    beam_lane_next(b1);
+                    beam_lane_next(b2);
+                }
+                if (STORE_J) {
+                    double* gdst = p.j_ion + grow0 * (long long)A + col0;
+                    const uint32_t row_bytes = (uint32_t)cols * 8u;
+                    fence_async_smem();
+                    __syncwarp();
+                    if (p.bulk_ok && bulk_rows_ok && ((rows_valid * row_bytes) & 15u) == 0) {
+                        if (lane == 0) bulk_store_1d(gdst, smem_u32(tile), rows_valid * row_bytes);
+                    } else if (p.bulk_ok && !bulk_rows_ok && bulk_panel_ok) {
+                        if (lane < rows_valid) bulk_store_1d(gdst + lane * (long long)A, smem_u32(tile + lane * cols), row_bytes);
+                    } else {   // odd row length with a ragged group or panels: plain coalesced stores
+                        for (int rr = 0; rr < rows_valid; ++rr)
+                            for (int cc = lane; cc < cols; cc += 32) __stcs(gdst + rr * (long long)A + cc, tile[rr * cols + cc]);
+                        __syncwarp();
+                    }
+                }
+            }
+        };
+        if (__any_sync(0xffffffffu, (flags & 2) != 0))
+            sweep(std::true_type{});
+        else
+            sweep(std::false_type{});
+
+        // quadrature partial sums of the sample's 4 lanes
+        num += __shfl_xor_sync(0xffffffffu, num, 1);
+        den += __shfl_xor_sync(0xffffffffu, den, 1);
+        num += __shfl_xor_sync(0xffffffffu, num, 2);
+        den += __shfl_xor_sync(0xffffffffu, den, 2);
+        const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+        if (q == 0) {
+            xr[0] = num;
+            xr[1] = den;
+            xr[2] = ((badmask >> qbase) & 0xFu) ? 1.0 : 0.0;
+        }
+    }
+    __syncwarp();
+
+    // ---------------- phase 3: one lane per sample ----------------
+    const double* xr = xch + lane * kXchPitch;
+    const bool bad = xr[2] != 0.0;
+    const bool late_fix = STORE_J && __any_sync(0xffffffffu, active && bad && !known_invalid);
+    if (STORE_J) {
+        if (late_fix) {   // order the bulk (async proxy) writes before the generic-proxy rewrite below
+            tma_wait_all();
+            fence_async_all();
+        } else {
+            tma_wait_read<0>();   // the staging tile must outlive the bulk reads
+        }
+        __syncwarp();
+    }
+    double cd = xr[0] / xr[1];              // plume.py:124 (NOT masked by `invalid`)
+    if (cd == CUDART_INF) cd = CUDART_NAN;  // plume.py:125
+    if (active) {
+        if (p.div_angle) p.div_angle[s] = acos(cd);
+        if (p.cos_div) p.cos_div[s] = cd;
+        if (p.t_c) p.t_c[s] = __dmul_rn(thrust, cd);
+        if (p.invalid) p.invalid[s] = (known_invalid || bad) ? 1 : 0;
+        if (STORE_J && bad && !known_invalid) {  // plume.py:106, rare
             double* row = p.j_ion + s * (long long)A;
             for (int i = 0; i < A; ++i) row[i] = kInvalidFill;
         }

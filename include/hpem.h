@@ -88,6 +88,11 @@ typedef struct hpem_outputs {
 #define HPEM_FLAG_NO_TMA 2u       /* recurrence kernel: stage j_ion through plain st.global instead of TMA tensor   \
                                      stores (always the case for odd angle counts: rows are not 16-byte aligned) */
 
+#define HPEM_FLAG_LANES1 4u       /* force the recurrence kernel with ONE lane per sample in the angle sweep (K1u,  \
+                                     32x16 TMA boxes); default for even angle counts */
+#define HPEM_FLAG_LANES4 8u       /* force the recurrence kernel with FOUR lanes per sample in the sweep (K1v,      \
+                                     whole rows per bulk store); default for odd angle counts */
+
 typedef struct hpem_grid hpem_grid; /* opaque */
 
 int hpem_abi_version(void);

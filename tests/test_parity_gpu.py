@@ -13,6 +13,9 @@ from tests import parity
 pytestmark = pytest.mark.gpu
 
 GOLDEN = sorted((Path(__file__).parent / 'golden').glob('*.npz'))
+# kernel variants: K1v (default, TMA / plain stores), K1u (one lane per sample), K1d (reference operation order)
+MODES = {'default': {}, 'lanes4': {'lanes4': True}, 'lanes4_stg': {'lanes4': True, 'no_tma': True},
+         'lanes1': {'lanes1': True}, 'lanes1_stg': {'lanes1': True, 'no_tma': True}, 'direct': {'direct': True}}
 
 
 def _models():
@@ -32,15 +35,14 @@ def _compare(out, g, inputs, torr, radii, label):
 
 
 @pytest.mark.parametrize('path', GOLDEN, ids=[p.stem for p in GOLDEN])
-@pytest.mark.parametrize('mode', ['fast', 'fast_stg', 'direct'])
+@pytest.mark.parametrize('mode', list(MODES))
 def test_golden_host_path(path, mode, cuda_device):
     """NumPy in -> NumPy out (hpem_eval_host), both kernels, every golden file."""
     _, _, plume_cathode = _models()
     g, meta, inputs = parity.load_golden(path)
     radii = g['sweep_radius']
     sweep = float(radii[0]) if radii.shape[0] == 1 else radii
-    out = plume_cathode(inputs, sweep, n_angles=meta['n_angles'], torr_2_pa=meta['torr_2_pa'], direct=mode == 'direct',
-                        no_tma=mode == 'fast_stg', extras=True)
+    out = plume_cathode(inputs, sweep, n_angles=meta['n_angles'], torr_2_pa=meta['torr_2_pa'], extras=True, **MODES[mode])
     assert isinstance(out['j_ion'], np.ndarray) and out['j_ion'].dtype == np.float64
     frac = _compare(out, g, inputs, meta['torr_2_pa'], radii, path.stem)
     assert frac > 0.98, f'only {frac:.4f} of j_ion meets the pure rel-1e-12 rule'
@@ -92,9 +94,8 @@ def test_against_oracle_seeded(n, n_angles, cuda_device):
         ref['V_cc'] = cathode_coupling_oracle(b, torr)['V_cc']
     g = {'j_ion': ref['j_ion'], 'div_angle': ref['div_angle'], 'T_c': ref['T_c'], 'cos_div': ref['_cos_div'],
          'invalid': ref['_invalid'], 'V_cc': ref['V_cc']}
-    for mode in ('fast', 'fast_stg', 'direct'):
-        out = plume_cathode(b, 1.0, n_angles=n_angles, torr_2_pa=torr, direct=mode == 'direct',
-                            no_tma=mode == 'fast_stg', extras=True)
+    for mode, kw in MODES.items():
+        out = plume_cathode(b, 1.0, n_angles=n_angles, torr_2_pa=torr, extras=True, **kw)
         _compare(out, g, b, torr, np.array([1.0]), f'n{n}_a{n_angles}_{mode}')
 
 

@@ -1,0 +1,143 @@
+// store_pattern.cu -- memory-system probe: how fast can TMA tensor stores stream a (N, A) fp64 matrix when each
+// warp walks along the columns of RB rows at a time (box = RB rows x CB cols)?  No arithmetic; isolates the
+// write path (TMA -> L2 -> HBM) from the kernel's compute.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o build/store_pattern tools/store_pattern.cu
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int BUFS>
+__global__ void __launch_bounds__(128) store_kernel(const __grid_constant__ CUtensorMap map, int rb, int cb, int n_col_chunks,
+                                                    long long n_row_groups, int delay) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* stage = smem + warp * BUFS * 4096;
+    for (int i = lane; i < BUFS * 4096 / 8; i += 32) reinterpret_cast<double*>(stage)[i] = 1.0 + i;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const long long g = (long long)blockIdx.x * 4 + warp;
+    if (g >= n_row_groups) return;
+    double acc = lane;
+    for (int c = 0; c < n_col_chunks; ++c) {
+        for (int d = 0; d < delay; ++d) acc = fma(acc, 1.0000001, 1e-9);   // stand-in for the per-chunk compute time
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&map),
+                         "r"(c * cb), "r"((int)(g * rb)), "r"(smem_u32(stage + (c % BUFS) * 4096))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(BUFS - 1) : "memory");
+        }
+        __syncwarp();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (acc == 1234.5) stage[0] = 1;
+}
+
+// mode B: per iteration lane 0 issues `m` back-to-back 32x16 boxes for ADJACENT column blocks (one commit group)
+__global__ void __launch_bounds__(128) store_multi_kernel(const __grid_constant__ CUtensorMap map, int m, int n_col_chunks,
+                                                          long long n_row_groups, int wait_all) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* stage = smem + warp * m * 4096;
+    for (int i = lane; i < m * 4096 / 8; i += 32) reinterpret_cast<double*>(stage)[i] = 1.0 + i;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const long long g = (long long)blockIdx.x * 4 + warp;
+    if (g >= n_row_groups) return;
+    for (int c = 0; c < n_col_chunks; c += m) {
+        if (lane == 0) {
+            for (int q = 0; q < m && c + q < n_col_chunks; ++q) {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&map),
+                             "r"((c + q) * 16), "r"((int)(g * 32)), "r"(smem_u32(stage + q * 4096))
+                             : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (wait_all) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+int main(int argc, char** argv) {
+    const long long N = 1000000;
+    const int A = argc > 1 ? atoi(argv[1]) : 256;
+    double* out;
+    cudaMalloc(&out, (size_t)N * A * 8);
+    void* fnp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &q);
+    EncodeTiledFn enc = (EncodeTiledFn)fnp;
+    cudaFuncSetAttribute(store_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(store_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int shapes[][2] = {{32, 16}, {16, 32}, {8, 64}, {4, 128}, {2, 256}};
+    for (int delay : {0, 400}) {
+        for (auto& sh : shapes) {
+            const int rb = sh[0], cb = sh[1];
+            if (cb > A) continue;
+            CUtensorMap map;
+            const cuuint64_t dims[2] = {(cuuint64_t)A, (cuuint64_t)N};
+            const cuuint64_t strides[1] = {(cuuint64_t)A * 8};
+            const cuuint32_t box[2] = {(cuuint32_t)cb, (cuuint32_t)rb};
+            const cuuint32_t es[2] = {1, 1};
+            CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { printf("encode failed %d for box %dx%d\n", (int)r, rb, cb); continue; }
+            const long long groups = (N + rb - 1) / rb;
+            const int chunks = (A + cb - 1) / cb;
+            const unsigned blocks = (unsigned)((groups + 3) / 4);
+            float best = 1e9;
+            for (int rep = 0; rep < 6; ++rep) {
+                cudaEventRecord(e0);
+                store_kernel<2><<<blocks, 128, 4 * 2 * 4096 + 1024>>>(map, rb, cb, chunks, groups, delay);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                float ms;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (rep > 0 && ms < best) best = ms;
+            }
+            cudaError_t err = cudaGetLastError();
+            printf("A=%d delay=%d box %2d rows x %3d cols: %.3f ms  %.0f GB/s  (%s)\n", A, delay, rb, cb, best,
+                   (double)N * A * 8 / best / 1e6, cudaGetErrorString(err));
+        }
+    }
+    {
+        cudaFuncSetAttribute(store_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        CUtensorMap map;
+        const cuuint64_t dims[2] = {(cuuint64_t)A, (cuuint64_t)N};
+        const cuuint64_t strides[1] = {(cuuint64_t)A * 8};
+        const cuuint32_t box[2] = {16, 32};
+        const cuuint32_t es[2] = {1, 1};
+        enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        const long long groups = (N + 31) / 32;
+        const int chunks = (A + 15) / 16;
+        for (int wait_all : {1, 0}) for (int m : {1, 2, 4, 8}) {
+            float best = 1e9;
+            for (int rep = 0; rep < 6; ++rep) {
+                cudaEventRecord(e0);
+                store_multi_kernel<<<(unsigned)((groups + 3) / 4), 128, 4 * m * 4096 + 1024>>>(map, m, chunks, groups, wait_all);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                float ms;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (rep > 0 && ms < best) best = ms;
+            }
+            printf("A=%d multi-issue m=%d x (32 rows x 16 cols) swizzle128, wait_%s: %.3f ms  %.0f GB/s (%s)\n", A, m,
+                   wait_all ? "all" : "prev", best, (double)N * A * 8 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    return 0;
+}
