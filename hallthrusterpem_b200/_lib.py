@@ -34,6 +34,7 @@ FLAG_LANES4 = 8
 EXPORTED_SYMBOLS = (
     'hpem_abi_version', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',
     'hpem_eval', 'hpem_eval_host', 'hpem_launch_count',
+    'hpem_moments_layout_query', 'hpem_moments_accumulate',
 )
 
 
@@ -47,7 +48,15 @@ class HpemOutputs(ctypes.Structure):
 
 
 class HpemMomentsSpec(ctypes.Structure):
-    _fields_ = [('n_bins', ctypes.c_int32), ('log10_lo', ctypes.c_double), ('log10_hi', ctypes.c_double)]
+    _fields_ = [('hist_angle_stride', ctypes.c_int32), ('hist_sub_bits', ctypes.c_int32),
+                ('hist_min_exp2', ctypes.c_int32), ('hist_max_exp2', ctypes.c_int32),
+                ('want_cathode', ctypes.c_int32), ('want_thrust', ctypes.c_int32)]
+
+
+class HpemMomentsLayout(ctypes.Structure):
+    _fields_ = [('n_sums', ctypes.c_int64), ('off_angle_sum', ctypes.c_int64), ('off_angle_sumsq', ctypes.c_int64),
+                ('off_hist', ctypes.c_int64), ('n_hist_angles', ctypes.c_int32), ('n_bins', ctypes.c_int32),
+                ('n_minmax', ctypes.c_int32), ('reserved', ctypes.c_int32)]
 
 
 class HpemError(RuntimeError):
@@ -115,6 +124,11 @@ def load() -> ctypes.CDLL:
         lib.hpem_eval.restype = i32
         lib.hpem_eval_host.argtypes = [vp, i64, ctypes.POINTER(HpemInputs), ctypes.POINTER(HpemOutputs), dbl, u32]
         lib.hpem_eval_host.restype = i32
+        lib.hpem_moments_layout_query.argtypes = [vp, ctypes.POINTER(HpemMomentsSpec), ctypes.POINTER(HpemMomentsLayout)]
+        lib.hpem_moments_layout_query.restype = i32
+        lib.hpem_moments_accumulate.argtypes = [vp, i64, ctypes.POINTER(HpemInputs), dbl, ctypes.POINTER(HpemMomentsSpec),
+                                                vp, vp, vp]
+        lib.hpem_moments_accumulate.restype = i32
         if lib.hpem_abi_version() != 1:
             raise HpemError(f'libhpem ABI version {lib.hpem_abi_version()} != 1')
         _lib = lib

@@ -64,6 +64,10 @@ struct Workspace {
     size_t j_cap = 0;  // elements
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     std::vector<cudaEvent_t> events;
+    double* d_partials = nullptr;  // K2 per-block partial vectors
+    size_t partials_cap = 0;
+    double* d_partial_minmax = nullptr;
+    size_t partial_minmax_cap = 0;
 };
 
 }  // namespace
@@ -78,6 +82,7 @@ struct hpem_grid {
     double* d_radii = nullptr;
     size_t smem_tma = 0, smem_stg = 0, smem_nostore = 0;  // dynamic shared memory of the K1u variants
     size_t smem_v_store = 0, smem_v_nostore = 0;          // ... and of K1v
+    int sm_count = 148;
     bool smem_ok = false;
     Workspace ws;
 };
@@ -252,6 +257,7 @@ int hpem_grid_create(int device, int n_angles, const double* alpha, const double
     g->n_angles_pad = (n_angles + hpem::kAnglePad - 1) / hpem::kAnglePad * hpem::kAnglePad;
     g->n_radii = n_radii;
     g->radius0 = radii[0];
+    cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device);
     g->h = alpha[1];
     // uniform <=> alpha[i] == i*alpha[1] to rounding (np.linspace(0, pi/2, A), plume.py:53)
     bool uni = (alpha[0] == 0.0) && (alpha[1] > 0.0);
@@ -310,6 +316,8 @@ int hpem_grid_destroy(hpem_grid* g) {
     for (auto& p : ws.d_small) if (p) cudaFree(p);
     if (ws.d_invalid) cudaFree(ws.d_invalid);
     if (ws.d_j) cudaFree(ws.d_j);
+    if (ws.d_partials) cudaFree(ws.d_partials);
+    if (ws.d_partial_minmax) cudaFree(ws.d_partial_minmax);
     for (auto e : ws.events) cudaEventDestroy(e);
     if (ws.s_compute) cudaStreamDestroy(ws.s_compute);
     if (ws.s_copy) cudaStreamDestroy(ws.s_copy);
@@ -449,6 +457,95 @@ int hpem_eval_host(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_ou
         HPEM_CUDA(cudaStreamSynchronize(ws.s_compute));
         HPEM_CUDA(cudaStreamSynchronize(ws.s_copy));
     }
+    return HPEM_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int moments_layout(const hpem_grid* g, const hpem_moments_spec* spec, hpem_moments_layout* lay) {
+    if (!g || !spec || !lay) return fail(HPEM_ERR_INVALID_ARG, "NULL argument");
+    if (g->n_radii != 1) return fail(HPEM_ERR_UNSUPPORTED, "the reduce-only pass supports a single sweep radius");
+    if (!(g->uniform && g->smem_ok)) return fail(HPEM_ERR_UNSUPPORTED, "the reduce-only pass needs the uniform angle grid");
+    const int st = spec->hist_angle_stride;
+    if (st < 0 || (st & (st - 1)) != 0) return fail(HPEM_ERR_INVALID_ARG, "hist_angle_stride must be 0 or a power of two");
+    if (spec->hist_sub_bits < 0 || spec->hist_sub_bits > 6) return fail(HPEM_ERR_INVALID_ARG, "hist_sub_bits must be in [0, 6]");
+    if (st > 0 && !(spec->hist_min_exp2 < spec->hist_max_exp2 && spec->hist_min_exp2 > -1000 && spec->hist_max_exp2 < 1000))
+        return fail(HPEM_ERR_INVALID_ARG, "need -1000 < hist_min_exp2 < hist_max_exp2 < 1000");
+    lay->n_hist_angles = st > 0 ? (g->n_angles + st - 1) / st : 0;
+    lay->n_bins = st > 0 ? ((spec->hist_max_exp2 - spec->hist_min_exp2) << spec->hist_sub_bits) + 2 : 0;
+    lay->off_angle_sum = hpem::kMomScalars;
+    lay->off_angle_sumsq = lay->off_angle_sum + g->n_angles;
+    lay->off_hist = lay->off_angle_sumsq + g->n_angles;
+    lay->n_sums = lay->off_hist + (int64_t)lay->n_hist_angles * lay->n_bins;
+    lay->n_minmax = 6;
+    lay->reserved = 0;
+    return HPEM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hpem_moments_layout_query(const hpem_grid* g, const hpem_moments_spec* spec, hpem_moments_layout* lay) {
+    return moments_layout(g, spec, lay);
+}
+
+int hpem_moments_accumulate(hpem_grid* g, int64_t n, const hpem_inputs* in, double torr_2_pa, const hpem_moments_spec* spec,
+                            double* sums, double* minmax, void* stream) {
+    hpem_moments_layout lay;
+    int rc = moments_layout(g, spec, &lay);
+    if (rc != HPEM_OK) return rc;
+    if (!in || !sums || !minmax) return fail(HPEM_ERR_INVALID_ARG, "inputs/sums/minmax must be non-NULL");
+    if (n < 0) return fail(HPEM_ERR_INVALID_ARG, "negative sample count");
+    if (n == 0) return HPEM_OK;
+    DeviceGuard guard(g->device);
+    if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", g->device);
+    using namespace hpem;
+    const int n_chunks = (g->n_angles + kChunk - 1) / kChunk;
+    const size_t smem = size_t(g->n_angles_pad) * sizeof(double2) + size_t(kWarpsM) * 32 * kTilePitch * sizeof(double) +
+                        size_t(kWarpsM) * n_chunks * kChunk * 2 * sizeof(double) +
+                        size_t(lay.n_hist_angles) * lay.n_bins * sizeof(unsigned);
+    if (smem > 200 * 1024)
+        return fail(HPEM_ERR_UNSUPPORTED, "histogram/angle configuration needs %zu bytes of shared memory (> 200 KiB): "
+                    "raise hist_angle_stride or lower hist_sub_bits", smem);
+    rc = set_smem(moments_kernel, smem);
+    if (rc != HPEM_OK) return rc;
+    const int64_t batches = (n + kThreadsM - 1) / kThreadsM;
+    const int blocks = (int)std::min<int64_t>(batches, (int64_t)g->sm_count * 4);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Workspace& ws = g->ws;
+    std::lock_guard<std::mutex> lock(ws.mu);
+    rc = grow(ws.d_partials, ws.partials_cap, (size_t)g->sm_count * 4 * (size_t)lay.n_sums);
+    if (rc == HPEM_OK) rc = grow(ws.d_partial_minmax, ws.partial_minmax_cap, (size_t)g->sm_count * 4 * 6);
+    if (rc != HPEM_OK) return rc;
+
+    hpem_outputs no_out = {};
+    EvalParams p;
+    fill_params(*g, *in, no_out, 0, n, torr_2_pa, p);
+    p.has_thrust = spec->want_thrust != 0;
+    MomentsParams m;
+    m.hist_stride = spec->hist_angle_stride;
+    m.want_cathode = spec->want_cathode;
+    m.hist_sub_bits = spec->hist_sub_bits;
+    m.hist_min_exp2 = spec->hist_min_exp2;
+    m.hist_max_exp2 = spec->hist_max_exp2;
+    m.n_hist_angles = lay.n_hist_angles;
+    m.n_bins = lay.n_bins;
+    m.n_sums = lay.n_sums;
+    m.off_angle_sum = lay.off_angle_sum;
+    m.off_angle_sumsq = lay.off_angle_sumsq;
+    m.off_hist = lay.off_hist;
+    m.partials = ws.d_partials;
+    m.partial_minmax = ws.d_partial_minmax;
+    moments_kernel<<<blocks, kThreadsM, smem, st>>>(p, m);
+    HPEM_CUDA(cudaGetLastError());
+    const int fthreads = 256;
+    moments_finalize_kernel<<<(unsigned)((lay.n_sums + fthreads - 1) / fthreads), fthreads, 0, st>>>(
+        ws.d_partials, ws.d_partial_minmax, blocks, lay.n_sums, sums, minmax);
+    HPEM_CUDA(cudaGetLastError());
+    g_launches.fetch_add(2, std::memory_order_relaxed);
     return HPEM_OK;
 }
 

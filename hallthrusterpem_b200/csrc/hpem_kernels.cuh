@@ -704,4 +704,247 @@ __global__ void __launch_bounds__(kThreadsD) eval_direct_kernel(const EvalParams
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2: reduce-only Monte-Carlo pass (no j_ion materialisation) -- sample moments and histograms
+// ---------------------------------------------------------------------------------------------
+// Same per-sample arithmetic and the same one-lane recurrence sweep as K1u, but instead of storing j_ion the
+// 32 samples x 16 angles tile is column-reduced in shared memory: per angle sum(j), sum(j^2) over samples, plus
+// log-linear histograms of j for every `hist_stride`-th angle (bin index = leading bits of the fp64 pattern: 2^sub_bits
+// bins per octave, no log10 evaluation).  Per-sample scalars (V_cc, div_angle, T_c) accumulate in registers.
+// Persistent blocks stride over the sample batches and emit ONE partial vector per block; a second kernel adds the
+// partials in block order, so results are bit-reproducible for a fixed launch geometry.  The packed result is what
+// the multi-GPU driver all-reduces (ncclSum over fp64; counts are stored as fp64, exact below 2^53).
+struct MomentsParams {
+    int hist_stride;      // power of two, 0 = no histograms
+    int want_cathode;     // accumulate V_cc moments (the six cathode inputs are read)
+    int hist_sub_bits;
+    int hist_min_exp2, hist_max_exp2;
+    int n_hist_angles, n_bins;
+    long long n_sums;     // doubles per partial vector
+    long long off_angle_sum, off_angle_sumsq, off_hist;
+    double* partials;     // [gridDim.x][n_sums]
+    double* partial_minmax;  // [gridDim.x][6]  (-min, max) x (V_cc, div_angle, T_c)
+};
+constexpr int kMomScalars = 12;  // n_samples n_invalid n_nonfinite_rows | {n_finite sum sumsq} x {V_cc div_angle T_c}
+constexpr int kThreadsM = 128;
+constexpr int kWarpsM = kThreadsM / 32;
+
+__device__ __forceinline__ int hist_bin(double j, const MomentsParams& m) {
+    // log-linear bin: octave from the exponent field, 2^sub_bits linear sub-bins from the leading mantissa bits.
+    // bin 0 = underflow (incl. zero/negative), n_bins-1 = overflow (incl. +inf); NaN rows never get here.
+    const int hi = __double2hiint(j);
+    if (hi < 0) return 0;
+    const int key = hi >> (20 - m.hist_sub_bits);                        // (biased exponent << sub_bits) | sub-bin
+    const int lo_key = (m.hist_min_exp2 + 1023) << m.hist_sub_bits;
+    const int b = key - lo_key + 1;
+    return min(max(b, 0), m.n_bins - 1);
+}
+
+__global__ void __launch_bounds__(kThreadsM, 4) moments_kernel(const EvalParams p, const MomentsParams m) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int A = p.n_angles;
+    const int n_chunks = (A + kChunk - 1) / kChunk;
+    const int a_pad = n_chunks * kChunk;
+    double2* wsm = reinterpret_cast<double2*>(smem_raw);                               // [n_angles_pad]
+    double* tiles = reinterpret_cast<double*>(wsm + p.n_angles_pad);                   // [warps][32][17]
+    double* acc_all = tiles + kWarpsM * 32 * kTilePitch;                               // [warps][a_pad][2]
+    unsigned* hist = reinterpret_cast<unsigned*>(acc_all + kWarpsM * a_pad * 2);       // [n_hist_angles][n_bins]
+    __shared__ double red[kWarpsM][kMomScalars + 6];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* tile = tiles + warp * 32 * kTilePitch;
+    double* acc = acc_all + warp * a_pad * 2;
+    for (int i = threadIdx.x; i < p.n_angles_pad; i += kThreadsM) wsm[i] = p.w[i];
+    for (int i = threadIdx.x; i < kWarpsM * a_pad * 2; i += kThreadsM) acc_all[i] = 0.0;
+    for (int i = threadIdx.x; i < m.n_hist_angles * m.n_bins; i += kThreadsM) hist[i] = 0u;
+    __syncthreads();
+
+    double sc[kMomScalars];
+#pragma unroll
+    for (int i = 0; i < kMomScalars; ++i) sc[i] = 0.0;
+    double mm[6] = {-CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF};
+    const bool want_cathode = m.want_cathode != 0;
+    const bool want_thrust = p.has_thrust;
+    const int col = lane & (kChunk - 1), half = lane >> 4;
+
+    for (long long b0 = (long long)blockIdx.x * kThreadsM; b0 < p.n; b0 += (long long)gridDim.x * kThreadsM) {
+        const long long s_raw = b0 + threadIdx.x;
+        const bool active = s_raw < p.n;
+        const long long s = active ? s_raw : p.n - 1;
+        if (b0 + warp * 32 >= p.n) continue;   // warp-uniform; no block-level barrier inside the loop
+
+        double x_in[kNumInputs];
+#pragma unroll
+        for (int q = 0; q < kNumInputs; ++q) {
+            const bool needed = (q == IN_P_b) || (q <= IN_P_T ? want_cathode : (q == IN_T ? want_thrust : true));
+            x_in[q] = needed ? load_in(p, q, s) : 0.0;
+        }
+        if (want_cathode) {
+            const double v = cathode_vcc(x_in[IN_P_b], x_in[IN_V_a], x_in[IN_T_e], x_in[IN_V_vac], x_in[IN_Pstar],
+                                         x_in[IN_P_T], p.torr);
+            if (active && v == v) {
+                sc[3] += 1.0; sc[4] += v; sc[5] = fma(v, v, sc[5]);
+                mm[0] = fmax(mm[0], -v); mm[1] = fmax(mm[1], v);
+            }
+        }
+        const SampleConsts k = plume_sample_consts(x_in[IN_P_b], x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3],
+                                                   x_in[IN_c4], x_in[IN_c5], p.torr);
+        double j_cex, base;
+        cex_terms(k.density, x_in[IN_sigma], x_in[IN_I_B0], p.radius0, j_cex, base);
+        BeamState b1, b2;
+        beam_init(b1, p.h, k.a1, __dmul_rn(base, k.amp1));
+        beam_init(b2, p.h, k.a2, __dmul_rn(base, k.amp2));
+        const bool known_invalid = (k.a1 <= 0.0);
+        // a row is non-finite iff one of its per-sample constants is (then every angle is NaN/inf): it is counted and
+        // contributes zeros to the per-angle sums; finite rows never produce a non-finite j_ion
+        const double probe = (b1.amp + b2.amp + j_cex) * 0.0 + (b1.x + b2.x) * 0.0;
+        const bool row_ok = active && (known_invalid ||   // alpha1 <= 0: the row is the finite 1e-20 fill whatever else is NaN
+                                       ((probe == 0.0) && !(b1.x == CUDART_INF) && !(b2.x == CUDART_INF)));
+        // plume.py:105-106: a sample with alpha1 <= 0 or any j_ion <= 0 has its whole row replaced by 1e-20.  Whether
+        // a non-positive j_ion exists must be known BEFORE the row is accumulated, so the (rare) samples that can have
+        // one -- negative amplitude or no CEX floor -- run a look-ahead sweep first.
+        bool invalid = known_invalid;
+        if (!known_invalid && !(b1.amp >= 0.0 && b2.amp >= 0.0 && j_cex > 0.0)) {
+            BeamState t1 = b1, t2 = b2;
+            bool any_bad = false;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int i0 = c * kChunk;
+                if (c != 0 && (c % kRestartChunks) == 0) {
+                    beam_restart(t1, i0);
+                    beam_restart(t2, i0);
+                }
+                double e1 = t1.amp * t1.ec, e2 = t2.amp * t2.ec, r1 = t1.rc, r2 = t2.rc;
+                for (int kk = 0; kk < kChunk && i0 + kk < A; ++kk) {
+                    any_bad |= ((e1 + e2) + j_cex <= 0.0);
+                    e1 *= r1; r1 *= t1.q;
+                    e2 *= r2; r2 *= t2.q;
+                }
+                beam_next_chunk(t1);
+                beam_next_chunk(t2);
+            }
+            invalid = any_bad;
+        }
+        double num = 0.0, den = 0.0;
+        const bool hist_on = m.hist_stride > 0 && row_ok;
+
+        for (int c = 0; c < n_chunks; ++c) {
+            const int i0 = c * kChunk;
+            if (c != 0 && (c % kRestartChunks) == 0) {
+                beam_restart(b1, i0);
+                beam_restart(b2, i0);
+            }
+            double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec;
+            double r1 = b1.rc, r2 = b2.rc;
+            double* my_row = tile + lane * kTilePitch;
+#pragma unroll
+            for (int kk = 0; kk < kChunk; ++kk) {
+                const double2 w = wsm[i0 + kk];      // zero beyond A
+                const double sum = e1 + e2;
+                den = fma(w.x, sum, den);
+                num = fma(w.y, sum, num);
+                const int i = i0 + kk;
+                const bool real = i < A;             // warp-uniform
+                const double j = invalid ? kInvalidFill : sum + j_cex;   // the value current_density() returns
+                my_row[kk] = (row_ok && real) ? j : 0.0;
+                if (hist_on && real && (i & (m.hist_stride - 1)) == 0)
+                    atomicAdd(&hist[(i / m.hist_stride) * m.n_bins + hist_bin(j, m)], 1u);
+                e1 *= r1; r1 *= b1.q;
+                e2 *= r2; r2 *= b2.q;
+            }
+            beam_next_chunk(b1);
+            beam_next_chunk(b2);
+            __syncwarp();
+            // column sums over the warp's 32 samples: 2 lanes per angle, 16 rows each
+            {
+                double s1 = 0.0, s2 = 0.0;
+                const double* tcol = tile + (half * 16) * kTilePitch + col;
+#pragma unroll
+                for (int rr = 0; rr < 16; ++rr) {
+                    const double v = tcol[rr * kTilePitch];
+                    s1 += v;
+                    s2 = fma(v, v, s2);
+                }
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                if (half == 0) {
+                    acc[(i0 + col) * 2 + 0] += s1;
+                    acc[(i0 + col) * 2 + 1] += s2;
+                }
+            }
+            __syncwarp();
+        }
+        double cd = num / den;
+        if (cd == CUDART_INF) cd = CUDART_NAN;
+        if (active) {
+            sc[0] += 1.0;
+            if (invalid) sc[1] += 1.0;
+            if (!row_ok) sc[2] += 1.0;
+            const double dv = acos(cd);
+            if (dv == dv) {
+                sc[6] += 1.0; sc[7] += dv; sc[8] = fma(dv, dv, sc[8]);
+                mm[2] = fmax(mm[2], -dv); mm[3] = fmax(mm[3], dv);
+            }
+            if (want_thrust) {
+                const double tc = __dmul_rn(x_in[IN_T], cd);
+                if (tc == tc) {
+                    sc[9] += 1.0; sc[10] += tc; sc[11] = fma(tc, tc, sc[11]);
+                    mm[4] = fmax(mm[4], -tc); mm[5] = fmax(mm[5], tc);
+                }
+            }
+        }
+    }
+    // ---- block reduction of the register accumulators, then one partial vector per block ----
+#pragma unroll
+    for (int i = 0; i < kMomScalars; ++i) {
+        double v = sc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double v = mm[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) red[warp][kMomScalars + i] = v;
+    }
+    __syncthreads();
+    double* out = m.partials + (long long)blockIdx.x * m.n_sums;
+    if (threadIdx.x < kMomScalars) {
+        double v = 0.0;
+        for (int w = 0; w < kWarpsM; ++w) v += red[w][threadIdx.x];
+        out[threadIdx.x] = v;
+    } else if (threadIdx.x < kMomScalars + 6) {
+        double v = -CUDART_INF;
+        for (int w = 0; w < kWarpsM; ++w) v = fmax(v, red[w][threadIdx.x]);
+        m.partial_minmax[(long long)blockIdx.x * 6 + (threadIdx.x - kMomScalars)] = v;
+    }
+    for (int i = threadIdx.x; i < A; i += kThreadsM) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int w = 0; w < kWarpsM; ++w) {
+            s1 += acc_all[(w * a_pad + i) * 2 + 0];
+            s2 += acc_all[(w * a_pad + i) * 2 + 1];
+        }
+        out[m.off_angle_sum + i] = s1;
+        out[m.off_angle_sumsq + i] = s2;
+    }
+    for (int i = threadIdx.x; i < m.n_hist_angles * m.n_bins; i += kThreadsM) out[m.off_hist + i] = double(hist[i]);
+}
+
+// sums[i] += sum over blocks (fixed order) of partials[b][i];  minmax[i] = max(minmax[i], max_b partial_minmax[b][i])
+__global__ void moments_finalize_kernel(const double* __restrict__ partials, const double* __restrict__ partial_minmax,
+                                        int n_blocks, long long n_sums, double* __restrict__ sums, double* __restrict__ minmax) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_sums) {
+        double v = 0.0;
+        for (int b = 0; b < n_blocks; ++b) v += partials[(long long)b * n_sums + i];
+        sums[i] += v;
+    }
+    if (i < 6 && minmax) {
+        double v = minmax[i];
+        for (int b = 0; b < n_blocks; ++b) v = fmax(v, partial_minmax[(long long)b * 6 + i]);
+        minmax[i] = v;
+    }
+}
+
 }  // namespace hpem

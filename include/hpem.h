@@ -122,6 +122,46 @@ int hpem_eval(const hpem_grid *grid, int64_t n, const hpem_inputs *in, const hpe
 int hpem_eval_host(hpem_grid *grid, int64_t n, const hpem_inputs *in, const hpem_outputs *out,
                    double torr_2_pa, uint32_t flags);
 
+/* ---- reduce-only Monte-Carlo pass: sample moments and histograms without materialising j_ion -------------------
+ * (the consumers of the reference's outputs take percentiles / moments over the sample axis:
+ *  tests/test_plume.py:50-52, scripts/gen_data.py:402-404).  Single radius only.
+ *
+ * sums buffer (float64, length layout.n_sums; counts are stored as float64 so ONE ncclSum all-reduce merges ranks):
+ *   [0] n_samples  [1] n_invalid (plume.py:105)  [2] n_nonfinite_rows (NaN/inf samples, excluded from angle sums)
+ *   [3..5] V_cc: n_finite, sum, sum of squares   [6..8] div_angle: same   [9..11] T_c: same
+ *   [off_angle_sum + i]   sum over samples of j_ion[:, i]      (values exactly as current_density() returns them,
+ *   [off_angle_sumsq + i] sum over samples of j_ion[:, i]^2     i.e. 1e-20 for invalid samples)
+ *   [off_hist + a*n_bins + b] histogram count of j_ion[:, a*hist_angle_stride] in bin b:
+ *        bin 0: j < 2^hist_min_exp2 (incl. <= 0);  bin n_bins-1: j >= 2^hist_max_exp2;  otherwise log-linear:
+ *        b = 1 + floor((log2-octave - hist_min_exp2) * 2^hist_sub_bits + linear sub-bin within the octave)
+ * minmax buffer (float64, length 6): (-min, max) of V_cc, div_angle, T_c -> merge ranks with ONE ncclMax all-reduce.
+ * Both buffers are ACCUMULATED into (call hpem_moments_accumulate once per chunk of samples); initialise sums to 0
+ * and minmax to -inf. */
+typedef struct hpem_moments_spec {
+    int32_t hist_angle_stride; /* power of two; histogram every stride-th angle; 0 = no histograms */
+    int32_t hist_sub_bits;     /* 2^sub_bits bins per octave, 0..6 */
+    int32_t hist_min_exp2;     /* first octave */
+    int32_t hist_max_exp2;     /* one past the last octave */
+    int32_t want_cathode;      /* accumulate V_cc moments (reads the six cathode inputs) */
+    int32_t want_thrust;       /* accumulate T_c moments (reads input T) */
+} hpem_moments_spec;
+
+typedef struct hpem_moments_layout {
+    int64_t n_sums;
+    int64_t off_angle_sum;
+    int64_t off_angle_sumsq;
+    int64_t off_hist;
+    int32_t n_hist_angles;
+    int32_t n_bins;
+    int32_t n_minmax; /* 6 */
+    int32_t reserved;
+} hpem_moments_layout;
+
+int hpem_moments_layout_query(const hpem_grid *grid, const hpem_moments_spec *spec, hpem_moments_layout *layout);
+/* DEVICE buffers, asynchronous on `stream`.  `sums` (layout.n_sums doubles) and `minmax` (6 doubles) are updated. */
+int hpem_moments_accumulate(hpem_grid *grid, int64_t n, const hpem_inputs *in, double torr_2_pa,
+                            const hpem_moments_spec *spec, double *sums, double *minmax, void *stream);
+
 /* Number of kernel launches issued by this process through the library (for bench accounting). */
 int64_t hpem_launch_count(void);
 
