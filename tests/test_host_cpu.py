@@ -1,0 +1,212 @@
+"""CPU tests (no GPU) of the host-side logic: quadrature weights, beam-integral table, input marshalling,
+C-ABI library surface, sharding, and the multi-rank merge over gloo."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_simpson_weights_match_scipy():
+    from scipy.integrate import simpson
+    from hallthrusterpem_b200.quadrature import angle_grid, fused_weights, simpson_weights
+    rng = np.random.default_rng(3)
+    for A in (2, 3, 4, 5, 91, 100, 200, 256, 512, 513):
+        x = angle_grid(A)
+        W = simpson(np.eye(A), x=x, axis=-1)
+        assert np.max(np.abs(simpson_weights(x) - W)) <= 4e-16 * np.max(np.abs(W))
+        xr = np.sort(rng.uniform(0, 2, A))
+        assert np.max(np.abs(simpson_weights(xr) - simpson(np.eye(A), x=xr, axis=-1))) < 1e-15
+        if A >= 3:
+            wd, wn = fused_weights(x)
+            f = np.exp(-(x / 0.4) ** 2) + 0.01
+            flipped = f[::-1]
+            assert abs(wd @ f / simpson(flipped * np.cos(x), x=x) - 1) < 1e-14
+            assert abs(wn @ f / simpson(flipped * np.cos(x) * np.sin(x), x=x) - 1) < 1e-14
+
+
+def _device_table():
+    txt = (ROOT / 'hallthrusterpem_b200' / 'csrc' / 'hpem_dtable.inc').read_text()
+    rows = re.findall(r'\{([^{}]+)\},', txt)
+    tab = np.array([[float.fromhex(v.strip()) for v in r.split(',')] for r in rows])
+    m = int(re.search(r'#define HPEM_DTAB_M (\d+)', txt).group(1))
+    umax = float(re.search(r'#define HPEM_DTAB_UMAX ([0-9.]+)', txt).group(1))
+    return tab, m, umax
+
+
+def test_beam_integral_table_matches_reference_closed_form():
+    """NumPy emulation of csrc/hpem_device.cuh::beam_integral (same Horner order) vs the oracle's complex-erfi form
+    (plume.py:64-85) over the whole domain the reference can evaluate."""
+    from oracle.ref_restated import _beam_integral
+    tab, m, umax = _device_table()
+    assert tab.shape == (64, 11) and m == 64
+
+    def d_tab(a):
+        aa = np.abs(a)
+        v = aa / (aa + 2.0) * (m / umax)
+        idx = np.minimum(v.astype(int), m - 1)
+        t = 2 * (v - idx) - 1
+        q = tab[idx, 0].copy()
+        for j in range(1, tab.shape[1]):
+            q = q * t + tab[idx, j]
+        return q * ((2 * np.pi) * aa * aa / (aa * aa + 2.0))
+
+    rng = np.random.default_rng(1)
+    a = np.concatenate([10 ** rng.uniform(-6, np.log10(53.28), 100000), rng.uniform(0.01, 16, 100000)])
+    with np.errstate(all='ignore'):
+        ref = _beam_integral(a).real
+    rel = np.abs(d_tab(a) / ref - 1)
+    assert rel.max() < 5e-14 and np.sqrt(np.mean(rel ** 2)) < 3e-15      # the reference itself is only good to ~1e-14
+    assert np.allclose(d_tab(-a[:100]), d_tab(a[:100]), rtol=0, atol=0)   # even in alpha, like the reference
+    mp = pytest.importorskip('mpmath')
+    mp.mp.dps = 40
+    for x in (1e-4, 0.021, 0.2, 0.9, 1.5707963, 7.0, 30.0, 53.0):
+        z = mp.mpc(x / 2, mp.pi / (2 * x))
+        truth = mp.pi ** mp.mpf(1.5) / 2 * x * mp.exp(-(mp.mpf(x) / 2) ** 2) * (2 * mp.erfi(mp.mpf(x) / 2) - 2 * mp.re(mp.erfi(z)))
+        assert abs(d_tab(np.array([x]))[0] / float(truth) - 1) < 1e-15
+
+
+def test_erfi_overflow_threshold_constant():
+    """csrc/hpem_device.cuh::kExpOverflow reproduces where the reference's normalisation turns non-finite."""
+    from oracle.ref_restated import _beam_integral
+    k = float.fromhex('0x1.62e42fefa39efp+9')
+    lo, hi = 53.28349511409265, 53.28349511409266
+    assert (lo / 2) ** 2 <= k < (hi / 2) ** 2
+    with np.errstate(all='ignore'):
+        v = _beam_integral(np.array([lo, hi]))
+    assert np.isfinite(v[0].real) and not np.isfinite(v[1].real)
+
+
+def test_c_abi_library_exports_declared_symbols():
+    """The shared library loads without a GPU and exports every function include/hpem.h declares."""
+    from hallthrusterpem_b200 import _lib
+    path = _lib.build_library()
+    header = (ROOT / 'include' / 'hpem.h').read_text()
+    declared = set(re.findall(r'^\s*(?:const\s+)?[A-Za-z_0-9]+\s*\*?\s*(hpem_[a-z_0-9]+)\s*\(', header, flags=re.M))
+    assert {'hpem_abi_version', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',
+            'hpem_eval', 'hpem_eval_host', 'hpem_launch_count', 'hpem_moments_layout_query',
+            'hpem_moments_accumulate'} == declared
+    assert set(_lib.EXPORTED_SYMBOLS) == declared
+    lib = ctypes.CDLL(str(path))
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.hpem_abi_version.restype = ctypes.c_int
+    assert lib.hpem_abi_version() == 1
+    assert ctypes.sizeof(_lib.HpemInputs) == 15 * 8 * 2 and ctypes.sizeof(_lib.HpemOutputs) == 6 * 8
+    assert ctypes.sizeof(_lib.HpemMomentsSpec) == 24 and ctypes.sizeof(_lib.HpemMomentsLayout) == 48
+
+
+def test_product_path_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from hallthrusterpem_b200.models import cathode_coupling, current_density
+    scal = {'P_b': 1e-5, 'c0': .1, 'c1': .7, 'c2': -8., 'c3': .2, 'c4': 1e20, 'c5': 1e16, 'sigma_cex': 55e-20, 'I_B0': 3}
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        current_density(scal)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        cathode_coupling({'P_b': 10e-6, 'V_a': 300, 'T_e': 3, 'V_vac': 30, 'Pstar': 20e-6, 'P_T': 50e-6})
+
+
+def test_product_does_not_import_the_oracle():
+    for py in (ROOT / 'hallthrusterpem_b200').rglob('*.py'):
+        assert not re.search(r'^\s*(from|import)\s+oracle\b', py.read_text(), flags=re.M), py
+
+
+def test_input_marshalling_broadcasts_like_numpy():
+    from hallthrusterpem_b200 import _lib
+    from hallthrusterpem_b200.engine import _Batch
+    rng = np.random.default_rng(0)
+    inputs = {'P_b': rng.random((4, 3)), 'c0': 0.3, 'c1': np.float64(0.5), 'c2': rng.random((4, 1)), 'c3': np.array([0.2]),
+              'c4': 1e20, 'c5': 1e16, 'sigma_cex': 55e-20, 'I_B0': rng.random(3), 'T': None, 'extra': 'ignored'}
+    b = _Batch(inputs, _lib.PLUME_INPUTS, optional=('T',))
+    assert b.out_shape == (4, 3) and b.n == 12 and not b.on_device and 'T' not in b.present
+    k = _lib.INPUT_NAMES.index
+    assert b.struct.ptr[k('c0')] is None and b.struct.scalar[k('c0')] == 0.3
+    assert b.struct.ptr[k('c3')] is None and b.struct.scalar[k('c3')] == 0.2          # size-1 array = scalar
+    c2 = np.ctypeslib.as_array(ctypes.cast(b.struct.ptr[k('c2')], ctypes.POINTER(ctypes.c_double)), shape=(12,))
+    assert np.array_equal(c2.reshape(4, 3), np.broadcast_to(inputs['c2'], (4, 3)))
+    ib = np.ctypeslib.as_array(ctypes.cast(b.struct.ptr[k('I_B0')], ctypes.POINTER(ctypes.c_double)), shape=(12,))
+    assert np.array_equal(ib.reshape(4, 3), np.broadcast_to(inputs['I_B0'], (4, 3)))
+    scal = _Batch({n: 1.0 for n in _lib.PLUME_INPUTS}, _lib.PLUME_INPUTS)
+    assert scal.out_shape == (1,) and scal.n == 1                                       # np.atleast_1d (plume.py:59)
+    with pytest.raises(KeyError):
+        _Batch({'P_b': 1.0}, _lib.PLUME_INPUTS)
+    with pytest.raises(ValueError):
+        _Batch(dict({n: 1.0 for n in _lib.PLUME_INPUTS}, P_b=np.ones(3), c0=np.ones(4)), _lib.PLUME_INPUTS)
+
+
+def test_synthetic_batches_and_sharding():
+    from hallthrusterpem_b200.synthetic import ALL_KEYS, h9_sweep_batch, shard_bounds, spt100_batch
+    b = spt100_batch(1000, 7)
+    assert tuple(b) == ALL_KEYS and all(v.shape == (1000,) and v.dtype == np.float64 for v in b.values())
+    assert np.array_equal(b['c1'], spt100_batch(1000, 7)['c1']) and not np.array_equal(b['c1'], spt100_batch(1000, 8)['c1'])
+    assert 1e-8 <= b['P_b'].min() and b['P_b'].max() <= 1e-4 and 0.1 <= b['c1'].min() and b['c1'].max() <= 0.9
+    h = h9_sweep_batch(101)
+    assert h['P_b'][0] == 0.0 and h['P_b'][-1] == 1e-4
+    for n, w in ((10, 3), (1_000_000, 8), (7, 8)):
+        spans = [shard_bounds(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b_[0] for a, b_ in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, n, n_angles, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from hallthrusterpem_b200.mc import HistogramSpec, Layout, merge_buffers
+    from hallthrusterpem_b200.synthetic import shard_bounds, spt100_batch
+    from oracle.moments_oracle import packed_moments
+    from oracle.ref_restated import cathode_coupling_oracle, current_density_oracle
+    layout = Layout(n_angles, HistogramSpec(angle_stride=8, sub_bits=2))
+    full = spt100_batch(n, 31)
+    lo, hi = shard_bounds(n, world, rank)
+    mine = {k: v[lo:hi] for k, v in full.items()}
+    with np.errstate(all='ignore'):
+        o = current_density_oracle(mine, 1.0, n_angles, with_coords=False, return_internals=True)
+        v = cathode_coupling_oracle(mine)['V_cc']
+    sums, minmax = packed_moments(layout, o['j_ion'], v, o['div_angle'], o['T_c'], o['_invalid'])
+    ts, tm = torch.from_numpy(sums), torch.from_numpy(minmax)
+    merge_buffers(ts, tm)
+    if rank == 0:
+        q.put((ts.numpy().copy(), tm.numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_merge_over_gloo_equals_single_rank():
+    """world_size 2 on CPU: shard -> per-rank packed moments -> merge (all-reduce SUM / MAX) == unsharded result."""
+    import torch.multiprocessing as mp
+    from hallthrusterpem_b200.mc import HistogramSpec, Layout, MomentsResult
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    from oracle.moments_oracle import packed_moments
+    from oracle.ref_restated import cathode_coupling_oracle, current_density_oracle
+    n, n_angles, world = 601, 100, 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (np.random.default_rng().integers(0, 2000))
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, int(port), n, n_angles, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    sums, minmax = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    layout = Layout(n_angles, HistogramSpec(angle_stride=8, sub_bits=2))
+    full = spt100_batch(n, 31)
+    with np.errstate(all='ignore'):
+        o = current_density_oracle(full, 1.0, n_angles, with_coords=False, return_internals=True)
+        v = cathode_coupling_oracle(full)['V_cc']
+    ref_s, ref_m = packed_moments(layout, o['j_ion'], v, o['div_angle'], o['T_c'], o['_invalid'])
+    np.testing.assert_allclose(sums, ref_s, rtol=1e-13)
+    assert np.array_equal(sums[layout.off_hist:], ref_s[layout.off_hist:]) and np.array_equal(minmax, ref_m)
+    res = MomentsResult(layout, sums, minmax)
+    assert res.n_samples == n and abs(res.scalar('V_cc')['mean'] - v.mean()) < 1e-12
+    np.testing.assert_allclose(res.j_mean, o['j_ion'].mean(axis=0), rtol=1e-12)
+    p = res.j_percentile([5, 50, 95])
+    ref_p = np.percentile(o['j_ion'][:, layout.hist_angle_index], [5, 50, 95], axis=0)
+    assert np.all(np.abs(p / ref_p - 1) < 0.3)          # 4 bins per octave -> <= 25 % bin width
