@@ -68,6 +68,33 @@ __global__ void __launch_bounds__(128) store_multi_kernel(const __grid_constant_
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// mode C: every lane streams ITS OWN row piece (cb columns) with a 1-D bulk copy from a padded shared-memory row;
+// 32 rows per warp (the thread-per-sample mapping), `bufs` tile buffers per warp
+__global__ void __launch_bounds__(128) store_rows_kernel(double* out, int A, int cb, int pitch, int n_col_chunks,
+                                                         long long n_rows, int bufs) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* stage = reinterpret_cast<double*>(smem) + (size_t)warp * bufs * 32 * pitch;
+    for (int i = lane; i < bufs * 32 * pitch; i += 32) stage[i] = 1.0 + i;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const long long row = ((long long)blockIdx.x * 4 + warp) * 32 + lane;
+    if (row - lane >= n_rows) return;
+    for (int c = 0; c < n_col_chunks; ++c) {
+        const int cols = min(cb, A - c * cb);
+        if (row < n_rows) {
+            double* g = out + row * A + (long long)c * cb;
+            const uint32_t src = smem_u32(stage + ((c % bufs) * 32 + lane) * pitch);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(src), "r"(cols * 8) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (bufs == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 int main(int argc, char** argv) {
     const long long N = 1000000;
     const int A = argc > 1 ? atoi(argv[1]) : 256;
@@ -137,6 +164,28 @@ int main(int argc, char** argv) {
             }
             printf("A=%d multi-issue m=%d x (32 rows x 16 cols) swizzle128, wait_%s: %.3f ms  %.0f GB/s (%s)\n", A, m,
                    wait_all ? "all" : "prev", best, (double)N * A * 8 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    {
+        cudaFuncSetAttribute(store_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        for (int bufs : {1, 2}) for (int cb : {16, 32, 64, 128}) {
+            const int pitch = cb + 2;
+            const size_t smem_bytes = (size_t)4 * bufs * 32 * pitch * 8;
+            if (smem_bytes > 200 * 1024) continue;
+            const int chunks = (A + cb - 1) / cb;
+            const unsigned blocks = (unsigned)((N + 127) / 128);
+            float best = 1e9;
+            for (int rep = 0; rep < 6; ++rep) {
+                cudaEventRecord(e0);
+                store_rows_kernel<<<blocks, 128, smem_bytes>>>(out, A, cb, pitch, chunks, N, bufs);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                float ms;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (rep > 0 && ms < best) best = ms;
+            }
+            printf("A=%d per-lane 1-D bulk rows: 32 rows x %3d cols per warp, bufs=%d (%zu KB smem/block): %.3f ms  %.0f GB/s (%s)\n", A,
+                   cb, bufs, smem_bytes / 1024, best, (double)N * A * 8 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
         }
     }
     return 0;
