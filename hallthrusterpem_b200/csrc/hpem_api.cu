@@ -166,7 +166,31 @@ int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store
     using namespace hpem;
     if (p.n <= 0) return HPEM_OK;
     const bool use_uniform = g.uniform && g.n_radii == 1 && g.smem_ok && !(flags & HPEM_FLAG_FORCE_DIRECT);
-    if (use_uniform || !plume) {
+    const bool use_multi = plume && store_j && g.uniform && g.n_radii > 1 && g.n_radii <= kMaxRadiiFast && g.smem_ok &&
+                           !(flags & HPEM_FLAG_FORCE_DIRECT);
+    if (use_multi) {   // K1r: several radii through the recurrence sweep
+        const unsigned blocks = (unsigned)((p.n + kThreadsU - 1) / kThreadsU);
+        const long long row_len = (long long)g.n_angles * g.n_radii;
+        const size_t rad_bytes = size_t(2) * g.n_radii * kThreadsU * sizeof(double);
+        const size_t wbytes = size_t(g.n_angles_pad) * sizeof(double2) + 1024;
+        const bool tma_ok = (row_len % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.j_ion) & 15u) == 0) &&
+                            !(flags & HPEM_FLAG_NO_TMA) && row_len < 2147483647LL;
+        CUtensorMap map;
+        std::memset(&map, 0, sizeof(map));
+        if (tma_ok) {
+            int rc = make_j_map(p.j_ion, (int)row_len, p.n, kChunk, 32, true, &map);
+            if (rc != HPEM_OK) return rc;
+            const size_t smem = wbytes + rad_bytes + size_t(kWarpsU) * kTmaBuffers * kTmaTileBytes;
+            rc = set_smem(eval_multi_radius_kernel<true>, smem);
+            if (rc != HPEM_OK) return rc;
+            eval_multi_radius_kernel<true><<<blocks, kThreadsU, smem, st>>>(p, map);
+        } else {
+            const size_t smem = wbytes + rad_bytes + size_t(kWarpsU) * 32 * kTilePitch * sizeof(double);
+            int rc = set_smem(eval_multi_radius_kernel<false>, smem);
+            if (rc != HPEM_OK) return rc;
+            eval_multi_radius_kernel<false><<<blocks, kThreadsU, smem, st>>>(p, map);
+        }
+    } else if (use_uniform || !plume) {
         const unsigned blocks = (unsigned)((p.n + kThreadsU - 1) / kThreadsU);
         CUtensorMap map;
         std::memset(&map, 0, sizeof(map));

@@ -308,6 +308,169 @@ __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_ker
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1r: several sweep radii (j_ion (n, A, R), radius fastest) -- thread per sample, recurrence sweep
+// ---------------------------------------------------------------------------------------------
+// plume.py:95-102 with R radii: only `decay`, `j_cex` and `base_density` depend on the radius, the Gaussian profiles do
+// not.  Each thread keeps base_rho and j_cex_rho of its sample in shared memory ([rho][thread], conflict-free), runs
+// ONE recurrence sweep over the angles and emits R values per angle: j = base_rho * (A1 E1 + A2 E2) + j_cex_rho.
+// The flattened (angle, radius) columns are staged 16 at a time exactly like K1u (32x16 TMA boxes over an
+// (n, A*R) tensor, or plain stores when A*R is odd).  The two Simpson sums are radius-independent up to the factor
+// base_rho, so they are accumulated once and scaled per radius at the end (0/0 = NaN for an opaque plume, as in NumPy).
+constexpr int kMaxRadiiFast = 48;   // 2 * R * 128 * 8 B of shared memory per block
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(kThreadsU, 3) eval_multi_radius_kernel(const EvalParams p,
+                                                                         const __grid_constant__ CUtensorMap jmap) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int kStageBytesPerWarp = USE_TMA ? kTmaBuffers * kTmaTileBytes : 32 * kTilePitch * 8;
+    const int R = p.n_radii, A = p.n_angles;
+    double* rad_base = reinterpret_cast<double*>(smem_al + kWarpsU * kStageBytesPerWarp);   // [R][kThreadsU]
+    double* rad_cex = rad_base + R * kThreadsU;                                              // [R][kThreadsU]
+    double2* wsm = reinterpret_cast<double2*>(rad_cex + R * kThreadsU);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    unsigned char* stage = smem_al + warp * kStageBytesPerWarp;
+    for (int i = tid; i < p.n_angles_pad; i += kThreadsU) wsm[i] = p.w[i];
+    __syncthreads();
+
+    const long long s_raw = (long long)blockIdx.x * kThreadsU + tid;
+    const bool active = s_raw < p.n;
+    const long long s = active ? s_raw : p.n - 1;
+    const long long warp_s0 = s_raw - lane;
+    if (warp_s0 >= p.n) return;
+
+    double x_in[kNumInputs];
+#pragma unroll
+    for (int q = 0; q < kNumInputs; ++q) {
+        const bool needed = (q == IN_P_b) || (q <= IN_P_T ? p.v_cc != nullptr : (q == IN_T ? p.t_c != nullptr : true));
+        x_in[q] = needed ? load_in(p, q, s) : 0.0;
+    }
+    if (p.v_cc) {
+        const double v = cathode_vcc(x_in[IN_P_b], x_in[IN_V_a], x_in[IN_T_e], x_in[IN_V_vac], x_in[IN_Pstar],
+                                     x_in[IN_P_T], p.torr);
+        if (active) p.v_cc[s] = v;
+    }
+    const SampleConsts k = plume_sample_consts(x_in[IN_P_b], x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3],
+                                               x_in[IN_c4], x_in[IN_c5], p.torr);
+    const bool known_invalid = (k.a1 <= 0.0);
+    bool needs_check = known_invalid || !(k.amp1 >= 0.0 && k.amp2 >= 0.0);
+    for (int rho = 0; rho < R; ++rho) {
+        double j_cex, base;
+        cex_terms(k.density, x_in[IN_sigma], x_in[IN_I_B0], __ldg(p.radii + rho), j_cex, base);
+        rad_base[rho * kThreadsU + tid] = base;
+        rad_cex[rho * kThreadsU + tid] = j_cex;
+        needs_check |= !(base >= 0.0 && j_cex > 0.0);
+    }
+    BeamState b1, b2;
+    beam_init(b1, p.h, k.a1, k.amp1);   // amplitudes WITHOUT base_density: it is applied per radius
+    beam_init(b2, p.h, k.a2, k.amp2);
+
+    bool bad = false;
+    double s_num = 0.0, s_den = 0.0;
+    const int n_chunks = (A + kChunk - 1) / kChunk;
+    const long long row_len = (long long)A * R;
+    const int rows_valid = (int)min((long long)32, p.n - warp_s0);
+    const int colq = lane & (kChunk - 1), rsub = lane >> 4;
+    long long col_done = 0;   // flattened columns already flushed
+    int fill = 0;             // columns in the current tile
+    int tile_it = 0;
+
+    auto flush = [&](int ncols) {
+        unsigned char* tile = USE_TMA ? stage + (tile_it % kTmaBuffers) * kTmaTileBytes : stage;
+        if (USE_TMA) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&jmap, smem_u32(tile), (int)col_done, (int)warp_s0);
+                tma_wait_read<kTmaBuffers - 1>();
+            }
+            __syncwarp();
+        } else {
+            __syncwarp();
+            const double* trow = reinterpret_cast<const double*>(tile) + rsub * kTilePitch + colq;
+            double* g = p.j_ion + (warp_s0 + rsub) * row_len + col_done + colq;
+            const bool col_ok = colq < ncols;
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+                if (col_ok && (2 * rr + rsub) < rows_valid) __stcs(g, trow[2 * rr * kTilePitch]);
+                g += 2 * row_len;
+            }
+            __syncwarp();
+        }
+        col_done += ncols;
+        ++tile_it;
+    };
+    auto put = [&](int pos, double v) {
+        if (USE_TMA) {
+            unsigned char* row = stage + (tile_it % kTmaBuffers) * kTmaTileBytes + lane * (kChunk * 8);
+            *reinterpret_cast<double*>(row + (((pos >> 1) ^ (lane & 7)) << 4) + ((pos & 1) << 3)) = v;
+        } else {
+            reinterpret_cast<double*>(stage)[lane * kTilePitch + pos] = v;
+        }
+    };
+
+    const bool checked = __any_sync(0xffffffffu, needs_check);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int i0 = c * kChunk;
+        if (c != 0 && (c % kRestartChunks) == 0) {
+            beam_restart(b1, i0);
+            beam_restart(b2, i0);
+        }
+        double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec;
+        double r1 = b1.rc, r2 = b2.rc;
+        const int kcount = min(kChunk, A - i0);
+        for (int kk = 0; kk < kcount; ++kk) {
+            const double2 w = wsm[i0 + kk];
+            const double g = e1 + e2;                      // A1 E1 + A2 E2
+            s_den = fma(w.x, g, s_den);
+            s_num = fma(w.y, g, s_num);
+            for (int rho = 0; rho < R; ++rho) {
+                const double j = fma(rad_base[rho * kThreadsU + tid], g, rad_cex[rho * kThreadsU + tid]);
+                if (checked) bad |= (j <= 0.0);
+                put(fill, known_invalid ? kInvalidFill : j);
+                if (++fill == kChunk) {
+                    flush(kChunk);
+                    fill = 0;
+                }
+            }
+            e1 *= r1; r1 *= b1.q;
+            e2 *= r2; r2 *= b2.q;
+        }
+        beam_next_chunk(b1);
+        beam_next_chunk(b2);
+    }
+    if (fill > 0) flush(fill);   // TMA clips columns >= A*R
+
+    const bool late_fix = __any_sync(0xffffffffu, bad && !known_invalid);
+    if (USE_TMA) {
+        if (late_fix) {
+            if (lane == 0) tma_wait_all();
+            fence_async_all();
+        } else if (lane == 0) {
+            tma_wait_read<0>();
+        }
+        __syncwarp();
+    }
+    if (active) {
+        for (int rho = 0; rho < R; ++rho) {
+            const double base = rad_base[rho * kThreadsU + tid];
+            double cd = __dmul_rn(base, s_num) / __dmul_rn(base, s_den);   // plume.py:122-124 per radius
+            if (cd == CUDART_INF) cd = CUDART_NAN;
+            const long long o = s * R + rho;
+            if (p.div_angle) p.div_angle[o] = acos(cd);
+            if (p.cos_div) p.cos_div[o] = cd;
+            if (p.t_c) p.t_c[o] = __dmul_rn(x_in[IN_T], cd);
+        }
+        if (p.invalid) p.invalid[s] = (known_invalid || bad) ? 1 : 0;
+        if (bad && !known_invalid) {
+            double* row = p.j_ion + s * row_len;
+            for (long long i = 0; i < row_len; ++i) row[i] = kInvalidFill;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1v: thread per sample for the per-sample work, FOUR lanes per sample for the angle sweep,
 //      whole rows staged in shared memory and written with ONE bulk (TMA) copy per 8 samples
 // ---------------------------------------------------------------------------------------------

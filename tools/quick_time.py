@@ -50,10 +50,33 @@ def time_host(n, A, reps=3):
               f'D2H {(A + 3) * 8 * n / t / 1e9:.1f} GB/s', flush=True)
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and '--multi' not in sys.argv:
     for n, A in ((1_000_000, 200), (1_000_000, 91), (4_000_000, 256), (1_000_000, 512)):
         time_dev(n, A)
         time_dev(n, A, no_tma=True)
         time_dev(n, A, want_j=False)
     time_dev(1_000_000, 200, direct=True)
     time_host(1_000_000, 200)
+
+
+def time_multi_radius(n=100_000, A=91, R=25, reps=5):
+    from hallthrusterpem_b200.engine import PreparedCall
+    b = {k: torch.as_tensor(v, device='cuda:0') for k, v in spt100_batch(n, 1).items()}
+    radii = np.linspace(1.0, 1.2, R)
+    for label, kw in (('K1r', {}), ('K1r-stg', {'no_tma': True}), ('K1d', {'direct': True})):
+        call = PreparedCall(b, want_cathode=False, want_plume=True, sweep_radius=radii, n_angles=A, **kw)
+        for _ in range(2):
+            call.run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for _ in range(reps):
+            e0.record(); call.run(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+        ms = float(np.median(ts))
+        print(f'multi-radius {label:8s} n={n} A={A} R={R}: {ms:.3f} ms  {n * A * R / ms / 1e6:.1f} G(sample x angle x radius)/s  '
+              f'{n * A * R * 8 / ms / 1e6:.0f} GB/s', flush=True)
+
+
+if __name__ == '__main__' and '--multi' in sys.argv:
+    time_multi_radius()
+    time_multi_radius(A=200, R=8)
