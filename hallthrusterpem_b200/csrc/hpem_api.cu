@@ -89,11 +89,20 @@ struct hpem_grid {
 
 namespace {
 
+// Opt a kernel in to large dynamic shared memory.  The attribute is per function (not per launch), so it is raised to
+// the device's opt-in maximum once instead of being set to each grid's own requirement (a later, smaller grid must not
+// lower the limit of a cached larger one).
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) {
-        HPEM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    }
+    int dev = 0, max_optin = 0;
+    HPEM_CUDA(cudaGetDevice(&dev));
+    HPEM_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cudaFuncAttributes attr;
+    HPEM_CUDA(cudaFuncGetAttributes(&attr, kernel));
+    const int max_dynamic = max_optin - (int)attr.sharedSizeBytes;   // static __shared__ counts against the same limit
+    if (bytes > (size_t)max_dynamic)
+        return fail(HPEM_ERR_UNSUPPORTED, "kernel needs %zu bytes of shared memory, device allows %d", bytes, max_dynamic);
+    HPEM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic));
     return HPEM_OK;
 }
 
@@ -162,6 +171,28 @@ int make_j_map(double* j_ion, int n_angles, long long n_rows, int box_cols, int 
     return HPEM_OK;
 }
 
+// 3-D view of j_ion for K1u: (16 angles inside a 128-byte column block, samples, column blocks); one box = kTmaCB
+// column blocks x 32 samples x 16 angles, read from [column block][sample][128 B] sub-tiles (128B swizzle).
+int make_j_map3(double* j_ion, int n_angles, long long n_rows, CUtensorMap* map) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(HPEM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const int n_blocks = n_angles / hpem::kChunk;
+    if (n_blocks < hpem::kTmaCB) {   // never used by the kernel (every group takes the 2-D path)
+        std::memset(map, 0, sizeof(*map));
+        return HPEM_OK;
+    }
+    // dimension order (angle within block, sample, column block): the box is laid out in shared memory with the FIRST
+    // dimension fastest, i.e. [column block][sample][16 angles] -- one 128B-swizzled 32x16 sub-tile per column block
+    const cuuint64_t dims[3] = {(cuuint64_t)hpem::kChunk, (cuuint64_t)n_rows, (cuuint64_t)n_blocks};
+    const cuuint64_t strides[2] = {(cuuint64_t)n_angles * sizeof(double), (cuuint64_t)hpem::kChunk * sizeof(double)};
+    const cuuint32_t box[3] = {(cuuint32_t)hpem::kChunk, 32u, (cuuint32_t)hpem::kTmaCB};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, j_ion, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HPEM_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+    return HPEM_OK;
+}
+
 int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store_j, uint32_t flags, cudaStream_t st) {
     using namespace hpem;
     if (p.n <= 0) return HPEM_OK;
@@ -192,8 +223,9 @@ int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store
         }
     } else if (use_uniform || !plume) {
         const unsigned blocks = (unsigned)((p.n + kThreadsU - 1) / kThreadsU);
-        CUtensorMap map;
+        CUtensorMap map, map3;
         std::memset(&map, 0, sizeof(map));
+        std::memset(&map3, 0, sizeof(map3));
         // TMA tensor stores need 16-byte aligned rows: even angle count and a 16-byte aligned base
         const bool tma_ok = store_j && (g.n_angles % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.j_ion) & 15u) == 0) &&
                             !(flags & HPEM_FLAG_NO_TMA);
@@ -201,16 +233,17 @@ int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store
         // one-lane sweep (K1u) is the faster kernel; for odd A the four-lane sweep with whole-row bulk stores (K1v) wins
         const bool lanes1 = (flags & HPEM_FLAG_LANES1) ? true : (flags & HPEM_FLAG_LANES4) ? false : (g.n_angles % 2 == 0);
         if (!plume) {
-            eval_uniform_kernel<false, false, false><<<blocks, kThreadsU, 0, st>>>(p, map);
+            eval_uniform_kernel<false, false, false><<<blocks, kThreadsU, 0, st>>>(p, map, map3);
         } else if (lanes1) {   // K1u: one lane per sample for the angle sweep as well (128-byte row pieces)
             if (!store_j) {
-                eval_uniform_kernel<true, false, false><<<blocks, kThreadsU, g.smem_nostore, st>>>(p, map);
+                eval_uniform_kernel<true, false, false><<<blocks, kThreadsU, g.smem_nostore, st>>>(p, map, map3);
             } else if (tma_ok) {
                 int rc = make_j_map(p.j_ion, g.n_angles, p.n, kChunk, 32, true, &map);
+                if (rc == HPEM_OK) rc = make_j_map3(p.j_ion, g.n_angles, p.n, &map3);
                 if (rc != HPEM_OK) return rc;
-                eval_uniform_kernel<true, true, true><<<blocks, kThreadsU, g.smem_tma, st>>>(p, map);
+                eval_uniform_kernel<true, true, true><<<blocks, kThreadsU, g.smem_tma, st>>>(p, map, map3);
             } else {
-                eval_uniform_kernel<true, true, false><<<blocks, kThreadsU, g.smem_stg, st>>>(p, map);
+                eval_uniform_kernel<true, true, false><<<blocks, kThreadsU, g.smem_stg, st>>>(p, map, map3);
             }
         } else {               // K1v: four lanes per sample in the sweep, whole rows per bulk store
             const unsigned vblocks = (unsigned)((p.n + kThreadsV - 1) / kThreadsV);
@@ -315,7 +348,7 @@ int hpem_grid_create(int device, int n_angles, const double* alpha, const double
     const size_t wbytes = size_t(g->n_angles_pad) * sizeof(double2) + 1024;  // + slack for the 1024-byte alignment
     g->smem_nostore = wbytes;
     g->smem_stg = wbytes + size_t(hpem::kWarpsU) * 32 * hpem::kTilePitch * sizeof(double);
-    g->smem_tma = wbytes + size_t(hpem::kWarpsU) * hpem::kTmaBuffers * hpem::kTmaTileBytes;
+    g->smem_tma = wbytes + size_t(hpem::kWarpsU) * hpem::kTmaBuffers * hpem::kTmaGroupBytes;
     const size_t xbytes = size_t(hpem::kWarpsV) * 32 * hpem::kXchPitch * sizeof(double);
     g->smem_v_nostore = wbytes + xbytes;
     g->smem_v_store = wbytes + xbytes + size_t(hpem::kWarpsV) * hpem::k1v_tile_bytes(n_angles);

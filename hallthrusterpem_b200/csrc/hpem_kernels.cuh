@@ -74,11 +74,20 @@ __device__ __forceinline__ double load_in(const EvalParams& p, int k, long long 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+__device__ __forceinline__ void tma_issue_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0),
                  "r"(c1), "r"(smem_src)
                  : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_issue_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(smem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+    tma_issue_2d(map, smem_src, c0, c1);
+    tma_commit();
 }
 template <int N>
 __device__ __forceinline__ void tma_wait_read() {
@@ -96,6 +105,11 @@ constexpr int kTmaTileBytes = 32 * kChunk * 8;  // 32 samples x 16 angles, dense
 #define HPEM_TMA_BUFFERS 2
 #endif
 constexpr int kTmaBuffers = HPEM_TMA_BUFFERS;
+#ifndef HPEM_TMA_CB
+#define HPEM_TMA_CB 2
+#endif
+constexpr int kTmaCB = HPEM_TMA_CB;   // K1u: 16-angle chunks (128-byte column blocks) written by ONE 3-D TMA op
+constexpr int kTmaGroupBytes = kTmaCB * kTmaTileBytes;
 
 struct BeamState {  // per-thread recurrence state of one Gaussian beam
     double ec, rc, gc;     // chunk-start profile value, chunk-start ratio, chunk-to-chunk factor
@@ -131,11 +145,12 @@ __device__ __forceinline__ void beam_next_chunk(BeamState& b) {
 #endif
 template <bool WANT_PLUME, bool STORE_J, bool USE_TMA>
 __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_kernel(const EvalParams p,
-                                                                 const __grid_constant__ CUtensorMap jmap) {
+                                                                 const __grid_constant__ CUtensorMap jmap,
+                                                                 const __grid_constant__ CUtensorMap jmap3) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // layout: [staging tiles (1024-byte aligned for the 128B TMA swizzle)] [fused weights]
     unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    constexpr int kStageBytesPerWarp = USE_TMA ? kTmaBuffers * kTmaTileBytes : 32 * kTilePitch * 8;
+    constexpr int kStageBytesPerWarp = USE_TMA ? kTmaBuffers * kTmaGroupBytes : 32 * kTilePitch * 8;
     constexpr int kStageBytes = STORE_J ? kWarpsU * kStageBytesPerWarp : 0;
     double2* wsm = reinterpret_cast<double2*>(smem_al + kStageBytes);
 
@@ -186,7 +201,7 @@ __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_ker
     double num = 0.0, den = 0.0;
 
     const int A = p.n_angles;
-    const int n_chunks = p.n_angles_pad / kChunk;
+    const int n_chunks = (A + kChunk - 1) / kChunk;
     const int rows_valid = (int)min((long long)32, p.n - warp_s0);
     const int col = lane & (kChunk - 1);
     const int rsub = lane >> 4;
@@ -202,7 +217,9 @@ __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_ker
             double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec;
             double r1 = b1.rc, r2 = b2.rc;
             const int kcount = min(kChunk, A - i0);
-            unsigned char* my_row = USE_TMA ? stage + (c % kTmaBuffers) * kTmaTileBytes + lane * (kChunk * 8)
+            // TMA staging: [buffer][column block within the group][32 rows][128 B, 16-byte chunks XOR-swizzled by row]
+            unsigned char* group_buf = stage + ((c / kTmaCB) % kTmaBuffers) * kTmaGroupBytes;
+            unsigned char* my_row = USE_TMA ? group_buf + (c % kTmaCB) * kTmaTileBytes + lane * (kChunk * 8)
                                             : stage + lane * (kTilePitch * 8);
             auto step = [&](double2 w, double& jout) {
                 const double sum = e1 + e2;    // j_beam + j_scat
@@ -250,14 +267,28 @@ __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_ker
 
             if (STORE_J) {
                 if (USE_TMA) {
-                    // one 32x16 box per warp and chunk; rows >= n and columns >= A are clipped by the tensor map
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&jmap, smem_u32(stage + (c % kTmaBuffers) * kTmaTileBytes), i0, (int)warp_s0);
-                        tma_wait_read<kTmaBuffers - 1>();   // the other buffer is free again
+                    // kTmaCB chunks are shipped by ONE 3-D TMA op: 32 rows x (kTmaCB x 128 B) contiguous row pieces
+                    // (6.2-6.5 TB/s on B200 against 5.6 TB/s for single 128-byte pieces, tools/store_pattern.cu).
+                    // A trailing group that is incomplete or holds the partial last column block goes out as 2-D
+                    // 32x16 boxes, whose tensor map clips columns >= A.  Rows >= n are clipped by both maps.
+                    const bool last_chunk = (c == n_chunks - 1);
+                    if ((c % kTmaCB) == kTmaCB - 1 || last_chunk) {
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int c_first = c - (c % kTmaCB);
+                            if (c_first + kTmaCB <= A / kChunk) {
+                                tma_issue_3d(&jmap3, smem_u32(group_buf), 0, (int)warp_s0, c_first);
+                            } else {
+                                for (int cc = c_first; cc <= c; ++cc)
+                                    tma_issue_2d(&jmap, smem_u32(group_buf + (cc - c_first) * kTmaTileBytes), cc * kChunk,
+                                                 (int)warp_s0);
+                            }
+                            tma_commit();
+                            tma_wait_read<kTmaBuffers - 1>();   // the other group buffer is free again
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 } else {
                     __syncwarp();
                     const double* trow = reinterpret_cast<const double*>(stage) + rsub * kTilePitch + col;

@@ -95,6 +95,39 @@ __global__ void __launch_bounds__(128) store_rows_kernel(double* out, int A, int
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// mode D: 3-D tensor view (16 cols, A/16 column blocks, N rows): ONE op writes `cbs` adjacent 128-byte column blocks of
+// `rows` rows from shared-memory sub-tiles laid out [column block][row][128 B] (each sub-tile 128B-swizzle friendly).
+// A warp owns 32 rows (thread-per-sample mapping) and buffers `cbs` chunks of 16 columns before storing.
+__global__ void __launch_bounds__(128) store_3d_kernel(const __grid_constant__ CUtensorMap map, int rows, int cbs, int n_colblocks,
+                                                       long long n_row_groups, int bufs, int order) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile_bytes = 32 * cbs * 128;                  // 32 rows x cbs column blocks
+    unsigned char* stage = smem + (size_t)warp * bufs * tile_bytes;
+    for (int i = lane; i < bufs * tile_bytes / 8; i += 32) reinterpret_cast<double*>(stage)[i] = 1.0 + i;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const long long g = (long long)blockIdx.x * 4 + warp;   // 32-row group
+    if (g >= n_row_groups) return;
+    int it = 0;
+    for (int cb0 = 0; cb0 + cbs <= n_colblocks; cb0 += cbs, ++it) {
+        if (lane == 0) {
+            unsigned char* buf = stage + (it % bufs) * tile_bytes;
+            for (int rg = 0; rg < 32 / rows; ++rg) {
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map),
+                             "r"(0), "r"(order ? (int)(g * 32 + rg * rows) : cb0), "r"(order ? cb0 : (int)(g * 32 + rg * rows)),
+                             "r"(smem_u32(buf + rg * rows * cbs * 128))
+                             : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (bufs == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 int main(int argc, char** argv) {
     const long long N = 1000000;
     const int A = argc > 1 ? atoi(argv[1]) : 256;
@@ -186,6 +219,42 @@ int main(int argc, char** argv) {
             }
             printf("A=%d per-lane 1-D bulk rows: 32 rows x %3d cols per warp, bufs=%d (%zu KB smem/block): %.3f ms  %.0f GB/s (%s)\n", A,
                    cb, bufs, smem_bytes / 1024, best, (double)N * A * 8 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    {
+        cudaFuncSetAttribute(store_3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        const int ncb = A / 16;
+        const int cfgs[][2] = {{32, 1}, {16, 2}, {8, 4}, {32, 2}, {16, 4}, {32, 4}, {8, 8}};   // {rows per op, column blocks per op}
+        for (int order : {0, 1}) for (int bufs : {1, 2}) for (auto& c : cfgs) {
+            const int rows = c[0], cbs = c[1];
+            if (order == 1 && rows != 32) continue;
+            const size_t smem_bytes = (size_t)4 * bufs * 32 * cbs * 128 + 1024;
+            if (smem_bytes > 200 * 1024) continue;
+            CUtensorMap map;
+            // order == 0: dims (cols16, column blocks, rows): smem [row][block][128 B], a row's pieces are emitted consecutively
+            // order == 1: dims (cols16, rows, column blocks): smem [block][row][128 B] (swizzle-friendly for thread-per-row writers)
+            const cuuint64_t dims[3] = {16, order ? (cuuint64_t)N : (cuuint64_t)ncb, order ? (cuuint64_t)ncb : (cuuint64_t)N};
+            const cuuint64_t strides[2] = {order ? (cuuint64_t)A * 8 : 128, order ? 128 : (cuuint64_t)A * 8};
+            const cuuint32_t box[3] = {16, order ? (cuuint32_t)rows : (cuuint32_t)cbs, order ? (cuuint32_t)cbs : (cuuint32_t)rows};
+            const cuuint32_t es[3] = {1, 1, 1};
+            CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { printf("3d encode failed %d\n", (int)r); continue; }
+            const long long groups = (N + 31) / 32;
+            float best = 1e9;
+            for (int rep = 0; rep < 6; ++rep) {
+                cudaEventRecord(e0);
+                store_3d_kernel<<<(unsigned)((groups + 3) / 4), 128, smem_bytes>>>(map, rows, cbs, ncb, groups, bufs, order);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                float ms;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (rep > 0 && ms < best) best = ms;
+            }
+            const int used_cb = ncb / cbs * cbs;
+            printf("A=%d 3-D[order %d] ops: %2d rows x %d col-blocks (%4d B pieces) per op, warp tile 32 rows x %3d cols, bufs=%d (%3zu KB/block): %.3f ms  %.0f GB/s (%s)\n",
+                   A, order, rows, cbs, cbs * 128, cbs * 16, bufs, smem_bytes / 1024, best, (double)N * used_cb * 128 / best / 1e6,
+                   cudaGetErrorString(cudaGetLastError()));
         }
     }
     return 0;
