@@ -34,7 +34,7 @@ FLAG_LANES4 = 8
 EXPORTED_SYMBOLS = (
     'hpem_abi_version', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',
     'hpem_eval', 'hpem_eval_host', 'hpem_launch_count',
-    'hpem_moments_layout_query', 'hpem_moments_accumulate',
+    'hpem_moments_layout_query', 'hpem_moments_accumulate', 'hpem_sample_inputs', 'hpem_moments_accumulate_sampled',
 )
 
 
@@ -57,6 +57,13 @@ class HpemMomentsLayout(ctypes.Structure):
     _fields_ = [('n_sums', ctypes.c_int64), ('off_angle_sum', ctypes.c_int64), ('off_angle_sumsq', ctypes.c_int64),
                 ('off_hist', ctypes.c_int64), ('n_hist_angles', ctypes.c_int32), ('n_bins', ctypes.c_int32),
                 ('n_minmax', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
+class HpemPrior(ctypes.Structure):
+    _fields_ = [('kind', ctypes.c_int32), ('reserved', ctypes.c_int32), ('a', ctypes.c_double), ('b', ctypes.c_double)]
+
+
+PRIOR_CONST, PRIOR_UNIFORM, PRIOR_LOGUNIFORM, PRIOR_NORMAL = 0, 1, 2, 3
 
 
 class HpemError(RuntimeError):
@@ -129,6 +136,12 @@ def load() -> ctypes.CDLL:
         lib.hpem_moments_accumulate.argtypes = [vp, i64, ctypes.POINTER(HpemInputs), dbl, ctypes.POINTER(HpemMomentsSpec),
                                                 vp, vp, vp]
         lib.hpem_moments_accumulate.restype = i32
+        u64 = ctypes.c_uint64
+        lib.hpem_sample_inputs.argtypes = [i32, i64, u64, u64, ctypes.POINTER(HpemPrior), ctypes.POINTER(vp), vp]
+        lib.hpem_sample_inputs.restype = i32
+        lib.hpem_moments_accumulate_sampled.argtypes = [vp, i64, u64, u64, ctypes.POINTER(HpemPrior), dbl,
+                                                        ctypes.POINTER(HpemMomentsSpec), vp, vp, vp]
+        lib.hpem_moments_accumulate_sampled.restype = i32
         if lib.hpem_abi_version() != 1:
             raise HpemError(f'libhpem ABI version {lib.hpem_abi_version()} != 1')
         _lib = lib

@@ -549,12 +549,12 @@ int hpem_moments_layout_query(const hpem_grid* g, const hpem_moments_spec* spec,
     return moments_layout(g, spec, lay);
 }
 
-int hpem_moments_accumulate(hpem_grid* g, int64_t n, const hpem_inputs* in, double torr_2_pa, const hpem_moments_spec* spec,
-                            double* sums, double* minmax, void* stream) {
+static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem::SamplerParams* sampler, double torr_2_pa,
+                       const hpem_moments_spec* spec, double* sums, double* minmax, void* stream) {
     hpem_moments_layout lay;
     int rc = moments_layout(g, spec, &lay);
     if (rc != HPEM_OK) return rc;
-    if (!in || !sums || !minmax) return fail(HPEM_ERR_INVALID_ARG, "inputs/sums/minmax must be non-NULL");
+    if ((!in && !sampler) || !sums || !minmax) return fail(HPEM_ERR_INVALID_ARG, "inputs/sums/minmax must be non-NULL");
     if (n < 0) return fail(HPEM_ERR_INVALID_ARG, "negative sample count");
     if (n == 0) return HPEM_OK;
     DeviceGuard guard(g->device);
@@ -570,7 +570,7 @@ int hpem_moments_accumulate(hpem_grid* g, int64_t n, const hpem_inputs* in, doub
     rc = set_smem(moments_kernel, smem);
     if (rc != HPEM_OK) return rc;
     const int64_t batches = (n + kThreadsM - 1) / kThreadsM;
-    const int blocks = (int)std::min<int64_t>(batches, (int64_t)g->sm_count * 4);
+    const int blocks = (int)std::min<int64_t>(batches, (int64_t)g->sm_count * 3);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Workspace& ws = g->ws;
     std::lock_guard<std::mutex> lock(ws.mu);
@@ -579,8 +579,9 @@ int hpem_moments_accumulate(hpem_grid* g, int64_t n, const hpem_inputs* in, doub
     if (rc != HPEM_OK) return rc;
 
     hpem_outputs no_out = {};
+    hpem_inputs no_in = {};
     EvalParams p;
-    fill_params(*g, *in, no_out, 0, n, torr_2_pa, p);
+    fill_params(*g, in ? *in : no_in, no_out, 0, n, torr_2_pa, p);
     p.has_thrust = spec->want_thrust != 0;
     MomentsParams m;
     m.hist_stride = spec->hist_angle_stride;
@@ -594,15 +595,67 @@ int hpem_moments_accumulate(hpem_grid* g, int64_t n, const hpem_inputs* in, doub
     m.off_angle_sum = lay.off_angle_sum;
     m.off_angle_sumsq = lay.off_angle_sumsq;
     m.off_hist = lay.off_hist;
+    m.sampled = sampler ? 1 : 0;
     m.partials = ws.d_partials;
     m.partial_minmax = ws.d_partial_minmax;
-    moments_kernel<<<blocks, kThreadsM, smem, st>>>(p, m);
+    SamplerParams sp_zero;
+    std::memset(&sp_zero, 0, sizeof(sp_zero));
+    moments_kernel<<<blocks, kThreadsM, smem, st>>>(p, m, sampler ? *sampler : sp_zero);
     HPEM_CUDA(cudaGetLastError());
     const int fthreads = 256;
     moments_finalize_kernel<<<(unsigned)((lay.n_sums + fthreads - 1) / fthreads), fthreads, 0, st>>>(
         ws.d_partials, ws.d_partial_minmax, blocks, lay.n_sums, sums, minmax);
     HPEM_CUDA(cudaGetLastError());
     g_launches.fetch_add(2, std::memory_order_relaxed);
+    return HPEM_OK;
+}
+
+static int fill_sampler(uint64_t seed, uint64_t first_index, const hpem_prior* priors, hpem::SamplerParams* sp) {
+    if (!priors) return fail(HPEM_ERR_INVALID_ARG, "priors must be non-NULL");
+    for (int k = 0; k < HPEM_N_INPUTS; ++k) {
+        const hpem_prior& q = priors[k];
+        if (q.kind < HPEM_PRIOR_CONST || q.kind > HPEM_PRIOR_NORMAL) return fail(HPEM_ERR_INVALID_ARG, "prior %d: unknown kind %d", k, q.kind);
+        if (q.kind == HPEM_PRIOR_LOGUNIFORM && !(q.a > 0.0 && q.b > 0.0)) return fail(HPEM_ERR_INVALID_ARG, "prior %d: LogUniform needs positive bounds", k);
+        sp->prior[k].kind = q.kind;
+        sp->prior[k].reserved = 0;
+        sp->prior[k].a = q.a;
+        sp->prior[k].b = q.b;
+    }
+    sp->seed = seed;
+    sp->first_index = first_index;
+    return HPEM_OK;
+}
+
+int hpem_moments_accumulate(hpem_grid* g, int64_t n, const hpem_inputs* in, double torr_2_pa, const hpem_moments_spec* spec,
+                            double* sums, double* minmax, void* stream) {
+    if (!in) return fail(HPEM_ERR_INVALID_ARG, "inputs must be non-NULL");
+    return moments_run(g, n, in, nullptr, torr_2_pa, spec, sums, minmax, stream);
+}
+
+int hpem_moments_accumulate_sampled(hpem_grid* g, int64_t n, uint64_t seed, uint64_t first_index, const hpem_prior* priors,
+                                    double torr_2_pa, const hpem_moments_spec* spec, double* sums, double* minmax, void* stream) {
+    hpem::SamplerParams sp;
+    int rc = fill_sampler(seed, first_index, priors, &sp);
+    if (rc != HPEM_OK) return rc;
+    return moments_run(g, n, nullptr, &sp, torr_2_pa, spec, sums, minmax, stream);
+}
+
+int hpem_sample_inputs(int device, int64_t n, uint64_t seed, uint64_t first_index, const hpem_prior* priors, double* const* out,
+                       void* stream) {
+    if (!out) return fail(HPEM_ERR_INVALID_ARG, "out must be non-NULL");
+    if (n < 0) return fail(HPEM_ERR_INVALID_ARG, "negative sample count");
+    hpem::SamplerParams sp;
+    int rc = fill_sampler(seed, first_index, priors, &sp);
+    if (rc != HPEM_OK) return rc;
+    if (n == 0) return HPEM_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", device);
+    const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    hpem::sample_inputs_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        sp, n, out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7], out[8], out[9], out[10], out[11], out[12], out[13],
+        out[14]);
+    HPEM_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return HPEM_OK;
 }
 

@@ -21,6 +21,7 @@
 #include <type_traits>
 
 #include "hpem_device.cuh"
+#include "hpem_sampler.cuh"
 
 namespace hpem {
 
@@ -916,6 +917,7 @@ struct MomentsParams {
     int n_hist_angles, n_bins;
     long long n_sums;     // doubles per partial vector
     long long off_angle_sum, off_angle_sumsq, off_hist;
+    int sampled;          // 1: inputs are drawn on the fly by the on-device sampler (no input arrays are read)
     double* partials;     // [gridDim.x][n_sums]
     double* partial_minmax;  // [gridDim.x][6]  (-min, max) x (V_cc, div_angle, T_c)
 };
@@ -934,7 +936,8 @@ __device__ __forceinline__ int hist_bin(double j, const MomentsParams& m) {
     return min(max(b, 0), m.n_bins - 1);
 }
 
-__global__ void __launch_bounds__(kThreadsM, 4) moments_kernel(const EvalParams p, const MomentsParams m) {
+__global__ void __launch_bounds__(kThreadsM, 3) moments_kernel(const EvalParams p, const MomentsParams m,
+                                                               const __grid_constant__ SamplerParams sp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int A = p.n_angles;
     const int n_chunks = (A + kChunk - 1) / kChunk;
@@ -968,10 +971,14 @@ __global__ void __launch_bounds__(kThreadsM, 4) moments_kernel(const EvalParams 
         if (b0 + warp * 32 >= p.n) continue;   // warp-uniform; no block-level barrier inside the loop
 
         double x_in[kNumInputs];
+        if (m.sampled) {
+            sample_inputs(sp, (unsigned long long)s, x_in);
+        } else {
 #pragma unroll
-        for (int q = 0; q < kNumInputs; ++q) {
-            const bool needed = (q == IN_P_b) || (q <= IN_P_T ? want_cathode : (q == IN_T ? want_thrust : true));
-            x_in[q] = needed ? load_in(p, q, s) : 0.0;
+            for (int q = 0; q < kNumInputs; ++q) {
+                const bool needed = (q == IN_P_b) || (q <= IN_P_T ? want_cathode : (q == IN_T ? want_thrust : true));
+                x_in[q] = needed ? load_in(p, q, s) : 0.0;
+            }
         }
         if (want_cathode) {
             const double v = cathode_vcc(x_in[IN_P_b], x_in[IN_V_a], x_in[IN_T_e], x_in[IN_V_vac], x_in[IN_Pstar],

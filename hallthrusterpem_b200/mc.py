@@ -159,6 +159,17 @@ class MonteCarloMoments:
                                                     ctypes.c_void_p(self.minmax.data_ptr()), ctypes.c_void_p(stream)))
         return batch.n
 
+    def accumulate_sampled(self, n: int, seed: int, first_index: int = 0, priors: dict | None = None) -> int:
+        """Add samples [first_index, first_index + n) of the global index space, drawn on the fly by the on-device
+        sampler (no input arrays exist); asynchronous on the current stream."""
+        from .sampler import SPT100_PRIORS, priors_struct
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.hpem_moments_accumulate_sampled(
+            self.grid.handle, int(n), int(seed), int(first_index), priors_struct(priors or SPT100_PRIORS), self.torr,
+            ctypes.byref(self.spec), ctypes.c_void_p(self.sums.data_ptr()), ctypes.c_void_p(self.minmax.data_ptr()),
+            ctypes.c_void_p(stream)))
+        return int(n)
+
     def merge(self, group=None) -> None:
         """The path's only collective: all-reduce the packed buffers over the ranks (no-op without a process group)."""
         merge_buffers(self.sums, self.minmax, group)

@@ -162,6 +162,28 @@ int hpem_moments_layout_query(const hpem_grid *grid, const hpem_moments_spec *sp
 int hpem_moments_accumulate(hpem_grid *grid, int64_t n, const hpem_inputs *in, double torr_2_pa,
                             const hpem_moments_spec *spec, double *sums, double *minmax, void *stream);
 
+/* ---- on-device sampler for the input priors (the step before the path: amisc `sample_inputs`, gen_data.py:238) ----
+ * Counter-based (Philox4x32-10): the inputs of global sample index i depend only on (seed, i), never on the shard,
+ * chunk or GPU that draws them. */
+#define HPEM_PRIOR_CONST 0      /* value a */
+#define HPEM_PRIOR_UNIFORM 1    /* U(a, b)            yml: U(a,b), Uniform(a,b), Relative(p) around a nominal */
+#define HPEM_PRIOR_LOGUNIFORM 2 /* LogUniform(a, b)   yml:253,261 */
+#define HPEM_PRIOR_NORMAL 3     /* Normal(mean a, std b) */
+typedef struct hpem_prior {
+    int32_t kind;
+    int32_t reserved;
+    double a, b;
+} hpem_prior;
+
+/* Draw samples [first_index, first_index + n) of every input k with out[k] != NULL into DEVICE arrays (n doubles). */
+int hpem_sample_inputs(int device, int64_t n, uint64_t seed, uint64_t first_index, const hpem_prior priors[HPEM_N_INPUTS],
+                       double *const out[HPEM_N_INPUTS], void *stream);
+/* Reduce-only pass whose inputs are drawn on the fly (no input arrays exist at all): equivalent to
+ * hpem_sample_inputs + hpem_moments_accumulate, bit for bit. */
+int hpem_moments_accumulate_sampled(hpem_grid *grid, int64_t n, uint64_t seed, uint64_t first_index,
+                                    const hpem_prior priors[HPEM_N_INPUTS], double torr_2_pa,
+                                    const hpem_moments_spec *spec, double *sums, double *minmax, void *stream);
+
 /* Number of kernel launches issued by this process through the library (for bench accounting). */
 int64_t hpem_launch_count(void);
 

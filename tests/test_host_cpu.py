@@ -88,7 +88,7 @@ def test_c_abi_library_exports_declared_symbols():
     declared = set(re.findall(r'^\s*(?:const\s+)?[A-Za-z_0-9]+\s*\*?\s*(hpem_[a-z_0-9]+)\s*\(', header, flags=re.M))
     assert {'hpem_abi_version', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',
             'hpem_eval', 'hpem_eval_host', 'hpem_launch_count', 'hpem_moments_layout_query',
-            'hpem_moments_accumulate'} == declared
+            'hpem_moments_accumulate', 'hpem_sample_inputs', 'hpem_moments_accumulate_sampled'} == declared
     assert set(_lib.EXPORTED_SYMBOLS) == declared
     lib = ctypes.CDLL(str(path))
     for name in declared:
@@ -97,6 +97,7 @@ def test_c_abi_library_exports_declared_symbols():
     assert lib.hpem_abi_version() == 1
     assert ctypes.sizeof(_lib.HpemInputs) == 15 * 8 * 2 and ctypes.sizeof(_lib.HpemOutputs) == 6 * 8
     assert ctypes.sizeof(_lib.HpemMomentsSpec) == 24 and ctypes.sizeof(_lib.HpemMomentsLayout) == 48
+    assert ctypes.sizeof(_lib.HpemPrior) == 24
 
 
 def test_product_path_fails_loudly_without_cuda():
@@ -151,6 +152,25 @@ def test_synthetic_batches_and_sharding():
         spans = [shard_bounds(n, w, r) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b_[0] for a, b_ in zip(spans, spans[1:]))
         assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_philox_known_answers_and_uniforms():
+    """The NumPy statement of the sampler's stream reproduces the published Philox4x32-10 known-answer vectors
+    (Random123 kat_vectors); the device code is the same function compiled by nvcc (tests/test_sampler_gpu.py)."""
+    from hallthrusterpem_b200.sampler import SPT100_PRIORS, apply_priors_numpy, philox4x32_10, philox_uniforms
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox4x32_10(*[[c] for c in ctr], *key)
+        assert tuple(int(x[0]) for x in got) == want
+    u = philox_uniforms(123, 10, 50000)
+    assert u.shape == (50000, 16) and 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 2e-3
+    assert np.array_equal(philox_uniforms(123, 1010, 100), u[1000:1100])       # index-addressed: shards line up
+    x = apply_priors_numpy(u, SPT100_PRIORS)
+    assert 1e-8 <= x['P_b'].min() and x['P_b'].max() <= 1e-4 and 200 <= x['V_a'].min() and x['V_a'].max() <= 400
+    assert abs(np.corrcoef(x['c0'], x['c1'])[0, 1]) < 0.02
 
 
 def _gloo_worker(rank, world, port, n, n_angles, q):

@@ -1,0 +1,55 @@
+"""GPU tests of the on-device prior sampler and the sampled reduce-only pass."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_sampler_matches_numpy_stream(cuda_device):
+    from hallthrusterpem_b200.sampler import SPT100_PRIORS, apply_priors_numpy, philox_uniforms, sample_inputs
+    n, seed, first = 20000, 987654321012345, 4_000_000_123
+    dev = sample_inputs(n, seed, first, device=0)
+    ref = apply_priors_numpy(philox_uniforms(seed, first, n))
+    assert set(dev) == set(SPT100_PRIORS)
+    for name, t in dev.items():
+        got = t.cpu().numpy()
+        kind, lo, hi = SPT100_PRIORS[name]
+        # the device uses one fma for lo + u*(hi-lo); near a sign change (c2) the error is absolute, ~ulp(max|bound|)
+        np.testing.assert_allclose(got, ref[name], rtol=2e-15 if kind == 'uniform' else 2e-14,
+                                   atol=2e-16 * max(abs(lo), abs(hi)) if kind == 'uniform' else 0)
+    # index-addressed: a later window of the same stream equals a slice of the earlier draw
+    again = sample_inputs(500, seed, first + 1000, device=0)
+    for name in dev:
+        assert np.array_equal(again[name].cpu().numpy(), dev[name][1000:1500].cpu().numpy())
+    # other kinds
+    pri = dict(SPT100_PRIORS, V_a=('const', 300.0, 0.0), T_e=('normal', 3.0, 0.5))
+    d2 = sample_inputs(200000, 5, 0, priors=pri, device=0)
+    te = d2['T_e'].cpu().numpy()
+    assert np.all(d2['V_a'].cpu().numpy() == 300.0) and abs(te.mean() - 3.0) < 5e-3 and abs(te.std() - 0.5) < 5e-3
+
+
+def test_sampled_moments_equal_sample_then_accumulate_and_are_shard_invariant(cuda_device):
+    import torch
+    from hallthrusterpem_b200.mc import HistogramSpec, MonteCarloMoments
+    from hallthrusterpem_b200.sampler import sample_inputs
+    n, seed, A = 30000, 42, 200
+    hist = HistogramSpec(angle_stride=8, sub_bits=3)
+    a = MonteCarloMoments(n_angles=A, hist=hist, device=0, torr=133.322)
+    a.accumulate_sampled(n, seed, 0)
+    b = MonteCarloMoments(n_angles=A, hist=hist, device=0, torr=133.322)
+    b.accumulate(sample_inputs(n, seed, 0, device=0))
+    torch.cuda.synchronize()
+    ra, rb = a.result(), b.result()
+    assert np.array_equal(ra.sums, rb.sums) and np.array_equal(ra.minmax, rb.minmax)     # same values, same kernel, same order
+    # three uneven shards of the same global index range, accumulated separately and merged by addition
+    parts = []
+    for lo, hi in ((0, 7001), (7001, 19000), (19000, n)):
+        m = MonteCarloMoments(n_angles=A, hist=hist, device=0, torr=133.322)
+        m.accumulate_sampled(hi - lo, seed, lo)
+        parts.append(m.result())
+    sums = sum(p.sums for p in parts)
+    L = a.layout
+    assert np.array_equal(sums[:3], ra.sums[:3]) and np.array_equal(sums[L.off_hist:], ra.sums[L.off_hist:])
+    np.testing.assert_allclose(sums, ra.sums, rtol=1e-12)
+    assert np.array_equal(np.max([p.minmax for p in parts], axis=0), ra.minmax)
+    assert ra.n_samples == n and ra.n_invalid == 0
