@@ -585,6 +585,8 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
     p.has_thrust = spec->want_thrust != 0;
     MomentsParams m;
     m.hist_stride = spec->hist_angle_stride;
+    m.hist_shift = 0;
+    while ((1 << m.hist_shift) < m.hist_stride) ++m.hist_shift;
     m.want_cathode = spec->want_cathode;
     m.hist_sub_bits = spec->hist_sub_bits;
     m.hist_min_exp2 = spec->hist_min_exp2;

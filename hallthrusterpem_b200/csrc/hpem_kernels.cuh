@@ -911,6 +911,7 @@ __global__ void __launch_bounds__(kThreadsD) eval_direct_kernel(const EvalParams
 // the multi-GPU driver all-reduces (ncclSum over fp64; counts are stored as fp64, exact below 2^53).
 struct MomentsParams {
     int hist_stride;      // power of two, 0 = no histograms
+    int hist_shift;       // log2(hist_stride)
     int want_cathode;     // accumulate V_cc moments (the six cathode inputs are read)
     int hist_sub_bits;
     int hist_min_exp2, hist_max_exp2;
@@ -1027,33 +1028,41 @@ __global__ void __launch_bounds__(kThreadsM, 3) moments_kernel(const EvalParams 
         }
         double num = 0.0, den = 0.0;
         const bool hist_on = m.hist_stride > 0 && row_ok;
+        if (!row_ok) {   // non-finite (or inactive shadow) row: contribute exact zeros to the per-angle sums, NaN to cos_div
+            b1.amp = b2.amp = 0.0;
+            b1.ec = b1.rc = b1.gc = b1.q = b1.qk = b1.hh = 1.0;
+            b2.ec = b2.rc = b2.gc = b2.q = b2.qk = b2.hh = 1.0;
+            b1.x = b2.x = 0.0;
+            j_cex = 0.0;
+        }
+        const double j_fill = row_ok ? kInvalidFill : 0.0;
+        double* my_row = tile + lane * kTilePitch;
 
         for (int c = 0; c < n_chunks; ++c) {
             const int i0 = c * kChunk;
-            if (c != 0 && (c % kRestartChunks) == 0) {
+            if (c != 0 && (c % kRestartChunks) == 0 && row_ok) {
                 beam_restart(b1, i0);
                 beam_restart(b2, i0);
             }
             double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec;
             double r1 = b1.rc, r2 = b2.rc;
-            double* my_row = tile + lane * kTilePitch;
 #pragma unroll
             for (int kk = 0; kk < kChunk; ++kk) {
                 const double2 w = wsm[i0 + kk];      // zero beyond A
                 const double sum = e1 + e2;
                 den = fma(w.x, sum, den);
                 num = fma(w.y, sum, num);
-                const int i = i0 + kk;
-                const bool real = i < A;             // warp-uniform
-                const double j = invalid ? kInvalidFill : sum + j_cex;   // the value current_density() returns
-                my_row[kk] = (row_ok && real) ? j : 0.0;
-                if (hist_on && real && (i & (m.hist_stride - 1)) == 0)
-                    atomicAdd(&hist[(i / m.hist_stride) * m.n_bins + hist_bin(j, m)], 1u);
+                my_row[kk] = invalid ? j_fill : sum + j_cex;   // the value current_density() returns (columns >= A are never read back)
                 e1 *= r1; r1 *= b1.q;
                 e2 *= r2; r2 *= b2.q;
             }
             beam_next_chunk(b1);
             beam_next_chunk(b2);
+            // histograms of the selected angles of this chunk (the angle is warp-uniform; one shared-memory atomic per sample)
+            if (hist_on) {
+                for (int i = (i0 + m.hist_stride - 1) & ~(m.hist_stride - 1); i < min(i0 + kChunk, A); i += m.hist_stride)
+                    atomicAdd(&hist[(i >> m.hist_shift) * m.n_bins + hist_bin(my_row[i - i0], m)], 1u);
+            }
             __syncwarp();
             // column sums over the warp's 32 samples: 2 lanes per angle, 16 rows each
             {
