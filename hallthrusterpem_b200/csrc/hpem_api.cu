@@ -62,8 +62,8 @@ struct Workspace {
     size_t invalid_cap = 0;
     double* d_j = nullptr;
     size_t j_cap = 0;  // elements
-    cudaStream_t s_compute = nullptr, s_copy = nullptr;
-    std::vector<cudaEvent_t> events;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_h2d = nullptr;
+    std::vector<cudaEvent_t> events, h2d_events;
     double* d_partials = nullptr;  // K2 per-block partial vectors
     size_t partials_cap = 0;
     double* d_partial_minmax = nullptr;
@@ -376,6 +376,8 @@ int hpem_grid_destroy(hpem_grid* g) {
     if (ws.d_partials) cudaFree(ws.d_partials);
     if (ws.d_partial_minmax) cudaFree(ws.d_partial_minmax);
     for (auto e : ws.events) cudaEventDestroy(e);
+    for (auto e : ws.h2d_events) cudaEventDestroy(e);
+    if (ws.s_h2d) cudaStreamDestroy(ws.s_h2d);
     if (ws.s_compute) cudaStreamDestroy(ws.s_compute);
     if (ws.s_copy) cudaStreamDestroy(ws.s_copy);
     if (g->d_w) cudaFree(g->d_w);
@@ -422,6 +424,7 @@ int hpem_eval_host(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_ou
     std::lock_guard<std::mutex> lock(ws.mu);
     if (!ws.s_compute) HPEM_CUDA(cudaStreamCreateWithFlags(&ws.s_compute, cudaStreamNonBlocking));
     if (!ws.s_copy) HPEM_CUDA(cudaStreamCreateWithFlags(&ws.s_copy, cudaStreamNonBlocking));
+    if (!ws.s_h2d) HPEM_CUDA(cudaStreamCreateWithFlags(&ws.s_h2d, cudaStreamNonBlocking));
 
     const int64_t A = g->n_angles, R = g->n_radii;
     // which inputs are needed
@@ -478,11 +481,23 @@ int hpem_eval_host(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_ou
             dout.j_ion = ws.d_j;
         }
 
-        // H2D of the per-sample inputs (compute stream, in order before the kernels)
-        for (int k = 0; k < HPEM_N_INPUTS; ++k) {
-            if (!din.ptr[k]) continue;
-            HPEM_CUDA(cudaMemcpyAsync(ws.d_in[k], in->ptr[k] + b0, (size_t)nb * sizeof(double), cudaMemcpyHostToDevice,
-                                      ws.s_compute));
+        // H2D of the per-sample inputs in segments of 8 chunks on their own stream: the upload of segment k+1 overlaps
+        // the kernels and the D2H of segment k (PCIe is full duplex)
+        const int64_t seg = chunk * 8;
+        const int64_t n_seg = (nb + seg - 1) / seg;
+        while ((int64_t)ws.h2d_events.size() < n_seg) {
+            cudaEvent_t e;
+            HPEM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ws.h2d_events.push_back(e);
+        }
+        for (int64_t sg = 0; sg < n_seg; ++sg) {
+            const int64_t first = sg * seg, count = std::min(seg, nb - first);
+            for (int k = 0; k < HPEM_N_INPUTS; ++k) {
+                if (!din.ptr[k]) continue;
+                HPEM_CUDA(cudaMemcpyAsync(ws.d_in[k] + first, in->ptr[k] + b0 + first, (size_t)count * sizeof(double),
+                                          cudaMemcpyHostToDevice, ws.s_h2d));
+            }
+            HPEM_CUDA(cudaEventRecord(ws.h2d_events[sg], ws.s_h2d));
         }
         const int64_t n_chunks = (nb + chunk - 1) / chunk;
         while ((int64_t)ws.events.size() < n_chunks) {
@@ -492,6 +507,7 @@ int hpem_eval_host(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_ou
         }
         for (int64_t c = 0; c < n_chunks; ++c) {
             const int64_t first = c * chunk, count = std::min(chunk, nb - first);
+            if (c % 8 == 0) HPEM_CUDA(cudaStreamWaitEvent(ws.s_compute, ws.h2d_events[c / 8], 0));
             hpem::EvalParams p;
             fill_params(*g, din, dout, first, count, torr_2_pa, p);
             rc = launch(*g, p, plume, dout.j_ion != nullptr, flags, ws.s_compute);
@@ -511,6 +527,7 @@ int hpem_eval_host(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_ou
         }
         if (out->invalid)
             HPEM_CUDA(cudaMemcpyAsync(out->invalid + b0, ws.d_invalid, (size_t)nb, cudaMemcpyDeviceToHost, ws.s_compute));
+        HPEM_CUDA(cudaStreamSynchronize(ws.s_h2d));
         HPEM_CUDA(cudaStreamSynchronize(ws.s_compute));
         HPEM_CUDA(cudaStreamSynchronize(ws.s_copy));
     }

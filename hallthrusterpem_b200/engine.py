@@ -246,9 +246,12 @@ class PreparedCall:
     def results(self) -> dict:
         res = dict(self.result)
         if self.want_plume:
-            coords = np.empty(self.batch.out_shape, dtype=object)   # plume.py:152-157 (C-speed fill, one shared ndarray)
-            coords.fill(self.grid.alpha)
-            res['j_ion_coords'] = coords
+            # plume.py:152-157: an object array of loop shape whose every element is the SAME angle-grid ndarray.  The
+            # reference fills it with a Python loop (O(n)); here it is a zero-stride (read-only) broadcast view of one
+            # 0-d object array -- same shape, dtype, element identity and indexing behaviour, O(1) to build.
+            cell = np.empty((), dtype=object)
+            cell[()] = self.grid.alpha
+            res['j_ion_coords'] = np.broadcast_to(cell, self.batch.out_shape)
         return res
 
 
