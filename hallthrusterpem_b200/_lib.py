@@ -81,19 +81,23 @@ def nvcc_command(out: Path = LIB_PATH) -> list[str]:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
-    """Compile csrc/*.cu into lib/libhpem.so for sm_100a (cross-compiles without a GPU)."""
+    """Compile csrc/*.cu into lib/libhpem.so for sm_100a (cross-compiles without a GPU).  Safe to call from several
+    processes at once (each builds to a private temporary file and renames it into place)."""
     sources = list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) + list(CSRC.glob('*.inc')) + [HEADER]
     if LIB_PATH.exists() and not force:
         newest = max(p.stat().st_mtime for p in sources)
         if LIB_PATH.stat().st_mtime >= newest:
             return LIB_PATH
     LIB_PATH.parent.mkdir(parents=True, exist_ok=True)
-    cmd = nvcc_command()
+    tmp = LIB_PATH.with_name(f'{LIB_PATH.name}.tmp.{os.getpid()}')
+    cmd = nvcc_command(tmp)
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)
     if verbose:
         print(res.stderr)
     return LIB_PATH
@@ -112,6 +116,12 @@ def load() -> ctypes.CDLL:
         if _lib is not None:
             return _lib
         path = Path(os.environ.get('HPEM_LIBRARY', LIB_PATH))
+        if 'HPEM_LIBRARY' not in os.environ and (shutil.which('nvcc') or Path('/usr/local/cuda/bin/nvcc').exists()):
+            try:                      # (re)build when missing or older than its sources -- this IS the product, not a fallback
+                build_library()
+            except Exception as exc:  # noqa: BLE001
+                if not path.exists():
+                    raise LibraryMissing(f'building {path} failed: {exc}') from exc
         if not path.exists():
             raise LibraryMissing(f'{path} not found: build it with `python __graft_entry__.py` '
                                  '(nvcc, sm_100a). hallthrusterpem_b200 has no CPU fallback.')

@@ -124,6 +124,35 @@ def test_fast_and_direct_kernels_agree_large(cuda_device):
     assert (ratio[wide] - 1).abs().max().item() < 5e-3
 
 
+def test_config3_h9_pressure_sweep_large(cuda_device):
+    """BASELINE config 3 shape (H9-style linear pressure sweep incl. P_b = 0, A = 256 -> even-count Simpson tail) at
+    2e6 samples on the device: recurrence kernels vs the direct kernel everywhere, vs the CPU oracle on a strided subsample."""
+    import torch
+    from hallthrusterpem_b200.synthetic import h9_sweep_batch
+    from oracle.ref_restated import current_density_oracle
+    _, current_density, _ = _models()
+    n, A = 2_000_000, 256
+    host = h9_sweep_batch(n, 77)
+    b = {k: torch.as_tensor(v, device='cuda:0') for k, v in host.items()}
+    fast = current_density(b, 1.0, n_angles=A, extras=True)
+    jf = fast['j_ion']
+    for kw in ({'direct': True}, {'lanes4': True}):
+        other = current_density(b, 1.0, n_angles=A, extras=True, **kw)
+        assert ((jf - other['j_ion']).abs() / other['j_ion'].abs()).max().item() < 3e-13
+        assert torch.equal(fast['invalid'], other['invalid'])
+        assert ((fast['cos_div'] - other['cos_div']).abs() / other['cos_div'].abs()).max().item() < 1e-13
+        del other
+    idx = np.arange(0, n, 997)
+    sub = {k: v[idx] for k, v in host.items()}
+    with np.errstate(all='ignore'):
+        ref = current_density_oracle(sub, 1.0, A, 133.322, with_coords=False, return_internals=True)
+    tidx = torch.as_tensor(idx, device='cuda:0')
+    parity.check_j_ion(jf[tidx].cpu().numpy(), ref['j_ion'], sub['I_B0'], [1.0], ref['_invalid'])
+    parity.check_rel(fast['cos_div'][tidx].cpu().numpy(), ref['_cos_div'], 'cos_div')
+    parity.check_rel(fast['T_c'][tidx].cpu().numpy(), ref['T_c'], 'T_c')
+    assert float(host['P_b'][0]) == 0.0 and torch.isfinite(jf[0]).all()
+
+
 def test_reference_unit_tests_restated(cuda_device):
     """The bodies of the reference's own tests (tests/test_plume.py:17-98, tests/test_cathode.py:8-31), seeded."""
     from scipy.integrate import simpson
