@@ -21,13 +21,23 @@ constexpr double kHalfPi = 1.57079632679489661923;
 // reference's normalisation is non-finite (-> NaN amplitudes, plume.py:64-85) once (a/2)^2 exceeds it.
 constexpr double kExpOverflow = 0x1.62e42fefa39efp+9;
 
-// D(a) = 2 pi int_0^{pi/2} exp(-(t/a)^2) sin t dt, the denominator of A1/A2 (plume.py:65-75).
-// Even in a; NaN at a == 0, for NaN input and in the reference's erfi-overflow domain |a| > 53.2835.
-__device__ __forceinline__ double beam_integral(double a) {
+// 1/y to ~1 ulp for finite y >= 2 (table index only; not used where the reference divides)
+__device__ __forceinline__ double rcp_fast(double y) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    r = fma(r, fma(-y, r, 1.0), r);
+    r = fma(r, fma(-y, r, 1.0), r);
+    return r;
+}
+
+// numer / D(a) with D(a) = 2 pi int_0^{pi/2} exp(-(t/a)^2) sin t dt, the denominator of A1/A2 (plume.py:64-85).
+// D is even in a; the result is NaN at a == 0, for NaN input and in the reference's erfi-overflow domain |a| > 53.2835.
+// D = q(u) * 2 pi a^2 / (a^2 + 2) (table, see tools/gen_dtable.py), so numer/D = numer (a^2 + 2) / (q 2 pi a^2): one division.
+__device__ __forceinline__ double beam_amplitude(double numer, double a) {
     const double aa = fabs(a);
     const double half = aa * 0.5;
     const double hx = half * half;
-    const double u = aa / (aa + 2.0);
+    const double u = aa * rcp_fast(aa + 2.0);
     const double v = u * (double(HPEM_DTAB_M) / HPEM_DTAB_UMAX);
     int idx = __double2int_rz(v);  // NaN -> 0
     idx = min(max(idx, 0), HPEM_DTAB_M - 1);
@@ -37,9 +47,9 @@ __device__ __forceinline__ double beam_integral(double a) {
 #pragma unroll
     for (int j = 1; j <= HPEM_DTAB_DEG; ++j) q = fma(q, t, c[j]);
     const double a2 = aa * aa;
-    double d = q * ((2.0 * kPi) * a2 / (a2 + 2.0));
-    if (!(hx <= kExpOverflow) || aa == 0.0) d = CUDART_NAN;
-    return d;
+    double amp = (numer * (a2 + 2.0)) / (q * ((2.0 * kPi) * a2));
+    if (!(hx <= kExpOverflow) || aa == 0.0) amp = CUDART_NAN;
+    return amp;
 }
 
 // cathode.py:26-37.  log(1 + x), not log1p, and the reference's rounding sequence.
@@ -80,8 +90,8 @@ __device__ __forceinline__ SampleConsts plume_sample_consts(double p_b, double c
     if (a1 > kHalfPi) a1 = kHalfPi;                        // plume.py:60 (no lower clip; NaN unchanged)
     k.a1 = a1;
     k.a2 = a1 / c1;                                        // plume.py:61
-    k.amp1 = __dadd_rn(1.0, -c0) / beam_integral(k.a1);    // plume.py:64-76
-    k.amp2 = c0 / beam_integral(k.a2);                     // plume.py:77-85
+    k.amp1 = beam_amplitude(__dadd_rn(1.0, -c0), k.a1);    // plume.py:64-76
+    k.amp2 = beam_amplitude(c0, k.a2);                     // plume.py:77-85
     return k;
 }
 

@@ -38,7 +38,7 @@ def _device_table():
 
 
 def test_beam_integral_table_matches_reference_closed_form():
-    """NumPy emulation of csrc/hpem_device.cuh::beam_integral (same Horner order) vs the oracle's complex-erfi form
+    """NumPy emulation of the table lookup in csrc/hpem_device.cuh::beam_amplitude (same Horner order) vs the oracle's complex-erfi form
     (plume.py:64-85) over the whole domain the reference can evaluate."""
     from oracle.ref_restated import _beam_integral
     tab, m, umax = _device_table()

@@ -227,7 +227,6 @@ int main(int argc, char** argv) {
         const int cfgs[][2] = {{32, 1}, {16, 2}, {8, 4}, {32, 2}, {16, 4}, {32, 4}, {8, 8}};   // {rows per op, column blocks per op}
         for (int order : {0, 1}) for (int bufs : {1, 2}) for (auto& c : cfgs) {
             const int rows = c[0], cbs = c[1];
-            if (order == 1 && rows != 32) continue;
             const size_t smem_bytes = (size_t)4 * bufs * 32 * cbs * 128 + 1024;
             if (smem_bytes > 200 * 1024) continue;
             CUtensorMap map;
