@@ -153,6 +153,43 @@ def test_config3_h9_pressure_sweep_large(cuda_device):
     assert float(host['P_b'][0]) == 0.0 and torch.isfinite(jf[0]).all()
 
 
+def test_more_than_2_31_elements_and_row_independence(cuda_device):
+    """2.5e7 samples x 91 angles = 2.3e9 elements (> 2^31, 18 GB): 64-bit indexing, and every row equals the row the
+    same inputs produce in a small batch (samples are independent; the kernels are deterministic per sample)."""
+    import torch
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    _, current_density, _ = _models()
+    n, A, m = 25_000_000, 91, 4096
+    small = spt100_batch(m, 314)
+    reps = -(-n // m)
+    big = {k: torch.as_tensor(v, device='cuda:0').repeat(reps)[:n].contiguous() for k, v in small.items()}
+    out = current_density(big, 1.0, n_angles=A)
+    ref = current_density({k: torch.as_tensor(v, device='cuda:0') for k, v in small.items()}, 1.0, n_angles=A)
+    assert out['j_ion'].shape == (n, A)
+    for start in (0, (n // m // 2) * m, (reps - 2) * m):
+        assert torch.equal(out['j_ion'][start:start + m], ref['j_ion'])
+        assert torch.equal(out['div_angle'][start:start + m], ref['div_angle'])
+    tail = n - (reps - 1) * m
+    assert torch.equal(out['j_ion'][(reps - 1) * m:], ref['j_ion'][:tail])
+    del out, big
+    torch.cuda.empty_cache()
+
+
+def test_concurrent_host_calls_from_threads(cuda_device):
+    """amisc may call the model from ThreadPoolExecutor workers (gen_data.py:448-460): concurrent calls on the same
+    grid handle return exactly what serial calls return."""
+    from concurrent.futures import ThreadPoolExecutor
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    _, _, plume_cathode = _models()
+    batches = [spt100_batch(20000 + 137 * i, 900 + i) for i in range(6)]
+    serial = [plume_cathode(b, 1.0, n_angles=100) for b in batches]
+    with ThreadPoolExecutor(4) as ex:
+        parallel = list(ex.map(lambda b: plume_cathode(b, 1.0, n_angles=100), batches))
+    for s, p in zip(serial, parallel):
+        for key in ('V_cc', 'j_ion', 'div_angle', 'T_c'):
+            assert np.array_equal(s[key], p[key]), key
+
+
 def test_reference_unit_tests_restated(cuda_device):
     """The bodies of the reference's own tests (tests/test_plume.py:17-98, tests/test_cathode.py:8-31), seeded."""
     from scipy.integrate import simpson
