@@ -80,7 +80,7 @@ struct hpem_grid {
     double2* d_w = nullptr;
     double* d_alpha = nullptr;
     double* d_radii = nullptr;
-    size_t smem_tma = 0, smem_stg = 0, smem_nostore = 0;  // dynamic shared memory of the K1u variants
+    size_t smem_tma = 0, smem_stg = 0, smem_nostore = 0, smem_rows = 0;  // dynamic shared memory of the K1u variants
     size_t smem_v_store = 0, smem_v_nostore = 0;          // ... and of K1v
     int sm_count = 148;
     bool smem_ok = false;
@@ -231,19 +231,27 @@ int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store
                             !(flags & HPEM_FLAG_NO_TMA);
         // default choice (measured on B200, tools/variant_sweep.py): TMA tensor stores need even A, and with them the
         // one-lane sweep (K1u) is the faster kernel; for odd A the four-lane sweep with whole-row bulk stores (K1v) wins
-        const bool lanes1 = (flags & HPEM_FLAG_LANES1) ? true : (flags & HPEM_FLAG_LANES4) ? false : (g.n_angles % 2 == 0);
+        // K1u whole-row mode pays off while the warp's 32 x A tile is small (<= 16 KB, A <= 63: 0.123 ms vs 0.163 ms for
+        // K1v at A = 51); at A = 91 the 23 KB tile leaves 8 warps per SM and K1v is faster (0.204 ms vs 0.220 ms)
+        const bool rows_fit = (g.n_angles % 2 == 1) && size_t(32) * g.n_angles * 8 <= 16 * 1024;
+        const bool lanes1 = (flags & HPEM_FLAG_LANES1) ? true : (flags & HPEM_FLAG_LANES4) ? false
+                                                                 : (g.n_angles % 2 == 0 || rows_fit);
         if (!plume) {
-            eval_uniform_kernel<false, false, false><<<blocks, kThreadsU, 0, st>>>(p, map, map3);
+            eval_uniform_kernel<false, false, kStoreStg><<<blocks, kThreadsU, 0, st>>>(p, map, map3);
         } else if (lanes1) {   // K1u: one lane per sample for the angle sweep as well (128-byte row pieces)
             if (!store_j) {
-                eval_uniform_kernel<true, false, false><<<blocks, kThreadsU, g.smem_nostore, st>>>(p, map, map3);
+                eval_uniform_kernel<true, false, kStoreStg><<<blocks, kThreadsU, g.smem_nostore, st>>>(p, map, map3);
             } else if (tma_ok) {
                 int rc = make_j_map(p.j_ion, g.n_angles, p.n, kChunk, 32, true, &map);
                 if (rc == HPEM_OK) rc = make_j_map3(p.j_ion, g.n_angles, p.n, &map3);
                 if (rc != HPEM_OK) return rc;
-                eval_uniform_kernel<true, true, true><<<blocks, kThreadsU, g.smem_tma, st>>>(p, map, map3);
+                eval_uniform_kernel<true, true, kStoreTma><<<blocks, kThreadsU, g.smem_tma, st>>>(p, map, map3);
+            } else if (rows_fit && !(flags & HPEM_FLAG_NO_TMA)) {   // small odd A: whole rows, one 1-D bulk store per warp
+                hpem::EvalParams pr = p;
+                pr.bulk_ok = (reinterpret_cast<uintptr_t>(p.j_ion) & 15u) == 0;
+                eval_uniform_kernel<true, true, kStoreRows><<<blocks, kThreadsU, g.smem_rows, st>>>(pr, map, map3);
             } else {
-                eval_uniform_kernel<true, true, false><<<blocks, kThreadsU, g.smem_stg, st>>>(p, map, map3);
+                eval_uniform_kernel<true, true, kStoreStg><<<blocks, kThreadsU, g.smem_stg, st>>>(p, map, map3);
             }
         } else {               // K1v: four lanes per sample in the sweep, whole rows per bulk store
             const unsigned vblocks = (unsigned)((p.n + kThreadsV - 1) / kThreadsV);
@@ -349,14 +357,17 @@ int hpem_grid_create(int device, int n_angles, const double* alpha, const double
     g->smem_nostore = wbytes;
     g->smem_stg = wbytes + size_t(hpem::kWarpsU) * 32 * hpem::kTilePitch * sizeof(double);
     g->smem_tma = wbytes + size_t(hpem::kWarpsU) * hpem::kTmaBuffers * hpem::kTmaGroupBytes;
+    g->smem_rows = wbytes + size_t(hpem::kWarpsU) * ((size_t(32) * n_angles * 8 + 15) & ~size_t(15));
     const size_t xbytes = size_t(hpem::kWarpsV) * 32 * hpem::kXchPitch * sizeof(double);
     g->smem_v_nostore = wbytes + xbytes;
     g->smem_v_store = wbytes + xbytes + size_t(hpem::kWarpsV) * hpem::k1v_tile_bytes(n_angles);
     g->smem_ok = std::max(std::max(g->smem_stg, g->smem_tma), g->smem_v_store) <= 200 * 1024;
     if (g->smem_ok) {
-        int rc = set_smem(hpem::eval_uniform_kernel<true, true, true>, g->smem_tma);
-        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, true, false>, g->smem_stg);
-        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, false, false>, g->smem_nostore);
+        int rc = set_smem(hpem::eval_uniform_kernel<true, true, hpem::kStoreTma>, g->smem_tma);
+        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, true, hpem::kStoreStg>, g->smem_stg);
+        if (rc == HPEM_OK && g->smem_rows <= 200 * 1024)
+            rc = set_smem(hpem::eval_uniform_kernel<true, true, hpem::kStoreRows>, g->smem_rows);
+        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, false, hpem::kStoreStg>, g->smem_nostore);
         if (rc == HPEM_OK) rc = set_smem(hpem::eval_lanes4_kernel<true>, g->smem_v_store);
         if (rc == HPEM_OK) rc = set_smem(hpem::eval_lanes4_kernel<false>, g->smem_v_nostore);
         if (rc != HPEM_OK) return cleanup(rc);

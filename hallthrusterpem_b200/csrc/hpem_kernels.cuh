@@ -92,6 +92,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sm
     tma_issue_2d(map, smem_src, c0, c1);
     tma_commit();
 }
+__device__ __forceinline__ void bulk_store_1d(double* gdst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 template <int N>
 __device__ __forceinline__ void tma_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -146,20 +151,29 @@ __device__ __forceinline__ void beam_next_chunk(BeamState& b) {
 #ifndef HPEM_MIN_BLOCKS_U
 #define HPEM_MIN_BLOCKS_U 6
 #endif
-template <bool WANT_PLUME, bool STORE_J, bool USE_TMA>
+// j_ion staging / store modes of K1u
+constexpr int kStoreStg = 0;    // 32x16 tile, transposed read-back, plain streaming stores (any A, any alignment)
+constexpr int kStoreTma = 1;    // 128B-swizzled sub-tiles, TMA tensor stores (even A, 16-byte aligned base)
+constexpr int kStoreRows = 2;   // whole rows of the warp's 32 samples (dense 32 x A tile), ONE contiguous 1-D bulk store
+                                // per warp: the mode for small odd A (the reference's 91), where no tensor map exists
+
+template <bool WANT_PLUME, bool STORE_J, int MODE>
 __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_kernel(const EvalParams p,
                                                                  const __grid_constant__ CUtensorMap jmap,
                                                                  const __grid_constant__ CUtensorMap jmap3) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // layout: [staging tiles (1024-byte aligned for the 128B TMA swizzle)] [fused weights]
     unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    constexpr int kStageBytesPerWarp = USE_TMA ? kTmaBuffers * kTmaGroupBytes : 32 * kTilePitch * 8;
-    constexpr int kStageBytes = STORE_J ? kWarpsU * kStageBytesPerWarp : 0;
-    double2* wsm = reinterpret_cast<double2*>(smem_al + kStageBytes);
+    constexpr bool USE_TMA = (MODE == kStoreTma);
+    constexpr bool ROWS = (MODE == kStoreRows);
+    const int stage_bytes_per_warp = USE_TMA ? kTmaBuffers * kTmaGroupBytes
+                                             : (ROWS ? ((32 * p.n_angles * 8 + 15) & ~15) : 32 * kTilePitch * 8);
+    const int stage_bytes = STORE_J ? kWarpsU * stage_bytes_per_warp : 0;
+    double2* wsm = reinterpret_cast<double2*>(smem_al + stage_bytes);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    unsigned char* stage = smem_al + warp * kStageBytesPerWarp;
+    unsigned char* stage = smem_al + warp * stage_bytes_per_warp;
 
     if (WANT_PLUME) {
         for (int i = threadIdx.x; i < p.n_angles_pad; i += kThreadsU) wsm[i] = p.w[i];
@@ -222,8 +236,9 @@ __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_ker
             const int kcount = min(kChunk, A - i0);
             // TMA staging: [buffer][column block within the group][32 rows][128 B, 16-byte chunks XOR-swizzled by row]
             unsigned char* group_buf = stage + ((c / kTmaCB) % kTmaBuffers) * kTmaGroupBytes;
+            // kStoreRows: dense [32][A] tile; for odd A the row pitch A*8 bytes walks all 16 bank pairs -> conflict-free
             unsigned char* my_row = USE_TMA ? group_buf + (c % kTmaCB) * kTmaTileBytes + lane * (kChunk * 8)
-                                            : stage + lane * (kTilePitch * 8);
+                                            : (ROWS ? stage + (size_t(lane) * A + i0) * 8 : stage + lane * (kTilePitch * 8));
             auto step = [&](double2 w, double& jout) {
                 const double sum = e1 + e2;    // j_beam + j_scat
                 const double j = sum + j_cex;  // plume.py:102
@@ -292,7 +307,7 @@ __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_ker
                         }
                         __syncwarp();
                     }
-                } else {
+                } else if (!ROWS) {
                     __syncwarp();
                     const double* trow = reinterpret_cast<const double*>(stage) + rsub * kTilePitch + col;
                     double* g = p.j_ion + (warp_s0 + rsub) * (long long)A + col + i0;
@@ -312,9 +327,22 @@ __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_ker
     else
         chunk_loop(std::false_type{});
 
+    if (STORE_J && ROWS) {   // ship the warp's rows: rows_valid * A * 8 contiguous bytes starting at a 16-byte aligned address
+        const uint32_t bytes = (uint32_t)rows_valid * (uint32_t)A * 8u;
+        double* gdst = p.j_ion + warp_s0 * (long long)A;
+        if (p.bulk_ok && (bytes & 15u) == 0) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) bulk_store_1d(gdst, smem_u32(stage), bytes);
+        } else {              // ragged last warp with an odd byte count, or a misaligned output: plain coalesced stores
+            __syncwarp();
+            const double* t = reinterpret_cast<const double*>(stage);
+            for (int e = lane; e < rows_valid * A; e += 32) __stcs(gdst + e, t[e]);
+        }
+    }
     // rare: a non-positive j_ion found after earlier chunks were already written -> the row is overwritten below
     const bool late_fix = STORE_J && __any_sync(0xffffffffu, bad && !known_invalid);
-    if (STORE_J && USE_TMA) {
+    if (STORE_J && (USE_TMA || ROWS)) {
         if (late_fix) {            // order the TMA (async proxy) writes before the generic-proxy rewrite
             if (lane == 0) tma_wait_all();
             fence_async_all();
@@ -533,11 +561,6 @@ constexpr int kAnglePad = kCols4;             // weights are zero-padded to a mu
 constexpr int kXch = 22;
 constexpr int kXchPitch = 23;                 // odd pitch: conflict-free column access
 
-__device__ __forceinline__ void bulk_store_1d(double* gdst, uint32_t smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
 
 // exp(-x*m) for the multipliers the stride-4 recurrence is assembled from
 __device__ __forceinline__ void beam_base_exps(double x, double* o) {
