@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = (
     'hpem_abi_version', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',
     'hpem_eval', 'hpem_eval_host', 'hpem_launch_count',
     'hpem_moments_layout_query', 'hpem_moments_accumulate', 'hpem_sample_inputs', 'hpem_moments_accumulate_sampled',
+    'hpem_measurements_create', 'hpem_measurements_destroy', 'hpem_loglike',
 )
 
 
@@ -152,6 +153,12 @@ def load() -> ctypes.CDLL:
         lib.hpem_moments_accumulate_sampled.argtypes = [vp, i64, u64, u64, ctypes.POINTER(HpemPrior), dbl,
                                                         ctypes.POINTER(HpemMomentsSpec), vp, vp, vp]
         lib.hpem_moments_accumulate_sampled.restype = i32
+        lib.hpem_measurements_create.argtypes = [vp, i32, dptr, dptr, dptr, ctypes.POINTER(vp)]
+        lib.hpem_measurements_create.restype = i32
+        lib.hpem_measurements_destroy.argtypes = [vp]
+        lib.hpem_measurements_destroy.restype = i32
+        lib.hpem_loglike.argtypes = [vp, vp, i64, ctypes.POINTER(HpemInputs), dbl, vp, vp, vp]
+        lib.hpem_loglike.restype = i32
         if lib.hpem_abi_version() != 1:
             raise HpemError(f'libhpem ABI version {lib.hpem_abi_version()} != 1')
         _lib = lib

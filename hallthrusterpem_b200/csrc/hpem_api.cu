@@ -80,6 +80,7 @@ struct hpem_grid {
     double2* d_w = nullptr;
     double* d_alpha = nullptr;
     double* d_radii = nullptr;
+    std::vector<double> alpha_host;
     size_t smem_tma = 0, smem_stg = 0, smem_nostore = 0, smem_rows = 0;  // dynamic shared memory of the K1u variants
     size_t smem_v_store = 0, smem_v_nostore = 0;          // ... and of K1v
     int sm_count = 148;
@@ -322,6 +323,7 @@ int hpem_grid_create(int device, int n_angles, const double* alpha, const double
     g->n_angles_pad = (n_angles + hpem::kAnglePad - 1) / hpem::kAnglePad * hpem::kAnglePad;
     g->n_radii = n_radii;
     g->radius0 = radii[0];
+    g->alpha_host.assign(alpha, alpha + n_angles);
     cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device);
     g->h = alpha[1];
     // uniform <=> alpha[i] == i*alpha[1] to rounding (np.linspace(0, pi/2, A), plume.py:53)
@@ -684,6 +686,112 @@ int hpem_sample_inputs(int device, int64_t n, uint64_t seed, uint64_t first_inde
     hpem::sample_inputs_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         sp, n, out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7], out[8], out[9], out[10], out[11], out[12], out[13],
         out[14]);
+    HPEM_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return HPEM_OK;
+}
+
+}  // extern "C"
+
+struct hpem_measurements {
+    int device = 0;
+    int m = 0, n_angles = 0;
+    hpem::MeasPoint* d_meas = nullptr;
+    int* d_seg = nullptr;
+};
+
+extern "C" {
+
+int hpem_measurements_create(const hpem_grid* g, int m, const double* theta, const double* y, const double* sigma,
+                             hpem_measurements** out) {
+    if (!out) return fail(HPEM_ERR_INVALID_ARG, "out handle pointer is NULL");
+    *out = nullptr;
+    if (!g || !theta || !y || !sigma) return fail(HPEM_ERR_INVALID_ARG, "NULL argument");
+    if (m < 1 || m > 4096) return fail(HPEM_ERR_INVALID_ARG, "number of measurement points must be in [1, 4096], got %d", m);
+    if (g->n_radii != 1 || !g->uniform) return fail(HPEM_ERR_UNSUPPORTED, "log-likelihood needs one radius and the uniform grid");
+    const int A = g->n_angles;
+    const std::vector<double>& al = g->alpha_host;
+    std::vector<hpem::MeasPoint> pts(m);
+    std::vector<int> lo(m);
+    for (int q = 0; q < m; ++q) {
+        const double a = std::fabs(theta[q]);
+        if (!(a <= al[A - 1])) return fail(HPEM_ERR_INVALID_ARG, "theta[%d] = %g is outside the sweep [-pi/2, pi/2]", q, theta[q]);
+        if (!(sigma[q] > 0.0)) return fail(HPEM_ERR_INVALID_ARG, "sigma[%d] must be positive", q);
+        // scipy.interpolate.interp1d: hi = clip(searchsorted(x, x_new, 'left'), 1, len-1), lo = hi - 1
+        int hi = (int)(std::lower_bound(al.begin(), al.end(), a) - al.begin());
+        hi = std::min(std::max(hi, 1), A - 1);
+        lo[q] = hi - 1;
+        pts[q].w = (a - al[hi - 1]) / (al[hi] - al[hi - 1]);
+        pts[q].y = y[q];
+        pts[q].inv_sigma = 1.0 / sigma[q];
+        pts[q].orig = q;
+        pts[q].pad = 0;
+    }
+    std::vector<int> order(m);
+    for (int q = 0; q < m; ++q) order[q] = q;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lo[a] < lo[b]; });
+    std::vector<hpem::MeasPoint> sorted(m);
+    std::vector<int> seg(A, m);
+    for (int r = 0; r < m; ++r) sorted[r] = pts[order[r]];
+    // seg[i] = first sorted point whose interval index is >= i
+    int r = 0;
+    for (int i = 0; i < A; ++i) {
+        while (r < m && lo[order[r]] < i) ++r;
+        seg[i] = r;
+    }
+    DeviceGuard guard(g->device);
+    if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", g->device);
+    hpem_measurements* h = new (std::nothrow) hpem_measurements();
+    if (!h) return fail(HPEM_ERR_CUDA, "out of host memory");
+    h->device = g->device;
+    h->m = m;
+    h->n_angles = A;
+    cudaError_t e = cudaMalloc((void**)&h->d_meas, sizeof(hpem::MeasPoint) * m);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_seg, sizeof(int) * A);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_meas, sorted.data(), sizeof(hpem::MeasPoint) * m, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_seg, seg.data(), sizeof(int) * A, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        hpem_measurements_destroy(h);
+        return fail(HPEM_ERR_CUDA, "measurement upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return HPEM_OK;
+}
+
+int hpem_measurements_destroy(hpem_measurements* h) {
+    if (!h) return HPEM_OK;
+    DeviceGuard guard(h->device);
+    if (h->d_meas) cudaFree(h->d_meas);
+    if (h->d_seg) cudaFree(h->d_seg);
+    delete h;
+    return HPEM_OK;
+}
+
+int hpem_loglike(const hpem_grid* g, const hpem_measurements* meas, int64_t n, const hpem_inputs* in, double torr_2_pa,
+                 double* loglike, double* y_pred, void* stream) {
+    if (!g || !meas || !in) return fail(HPEM_ERR_INVALID_ARG, "NULL argument");
+    if (!loglike && !y_pred) return fail(HPEM_ERR_INVALID_ARG, "no output requested");
+    if (meas->device != g->device || meas->n_angles != g->n_angles)
+        return fail(HPEM_ERR_INVALID_ARG, "measurement handle was created for another grid");
+    if (n < 0) return fail(HPEM_ERR_INVALID_ARG, "negative sample count");
+    if (n == 0) return HPEM_OK;
+    DeviceGuard guard(g->device);
+    if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", g->device);
+    using namespace hpem;
+    hpem_outputs no_out = {};
+    EvalParams p;
+    fill_params(*g, *in, no_out, 0, n, torr_2_pa, p);
+    LoglikeParams lp;
+    lp.m = meas->m;
+    lp.seg_start = meas->d_seg;
+    lp.meas = meas->d_meas;
+    lp.loglike = loglike;
+    lp.y_pred = y_pred;
+    const size_t smem = sizeof(MeasPoint) * meas->m + sizeof(int) * g->n_angles;
+    int rc = set_smem(loglike_kernel, smem);
+    if (rc != HPEM_OK) return rc;
+    const unsigned blocks = (unsigned)((n + kThreadsL - 1) / kThreadsL);
+    loglike_kernel<<<blocks, kThreadsL, smem, static_cast<cudaStream_t>(stream)>>>(p, lp);
     HPEM_CUDA(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return HPEM_OK;

@@ -1182,4 +1182,105 @@ __global__ void moments_finalize_kernel(const double* __restrict__ partials, con
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3: j_ion interpolated to measurement angles + Gaussian log-likelihood, without materialising j_ion
+// ---------------------------------------------------------------------------------------------
+// The step right after the plume model in the reference's calibration scripts: mirror the sweep to (-90, 90) deg,
+// `interp1d` (linear) to the probe angles (scripts/pem_v0/monte_carlo.py:265-270; the same intent is sketched in
+// plume.py:142-149), then sum -0.5 ((y - y_hat)/sigma)^2 (scripts/pem_v0/mcmc.py:103).  One thread per sample runs the
+// recurrence sweep once; the measurement points are pre-sorted by |angle| on the host so that the points falling in
+// grid interval [i-1, i] are a contiguous range that is consumed when the sweep reaches angle i.
+struct MeasPoint {       // one probe location, sorted by |theta|
+    double w;            // (|theta| - alpha[lo]) / (alpha[lo+1] - alpha[lo])
+    double y;            // measured j_ion
+    double inv_sigma;    // 1 / standard deviation
+    int orig;            // index in the caller's arrays
+    int pad;
+};
+struct LoglikeParams {
+    int m;                    // number of measurement points
+    const int* seg_start;     // [A]: points of interval [i, i+1] are seg_start[i] .. seg_start[i+1]-1 (seg_start[A-1] = m)
+    const MeasPoint* meas;    // [m] sorted
+    double* loglike;          // (n)   or nullptr
+    double* y_pred;           // (n, m) in the caller's point order, or nullptr
+};
+constexpr int kThreadsL = 128;
+
+__global__ void __launch_bounds__(kThreadsL) loglike_kernel(const EvalParams p, const LoglikeParams lp) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    MeasPoint* msm = reinterpret_cast<MeasPoint*>(smem_raw);                       // [m]
+    int* seg = reinterpret_cast<int*>(msm + lp.m);                                 // [A]
+    const int A = p.n_angles;
+    for (int i = threadIdx.x; i < lp.m; i += kThreadsL) msm[i] = lp.meas[i];
+    for (int i = threadIdx.x; i < A; i += kThreadsL) seg[i] = lp.seg_start[i];
+    __syncthreads();
+    const long long s = (long long)blockIdx.x * kThreadsL + threadIdx.x;
+    if (s >= p.n) return;
+
+    double x_in[kNumInputs];
+#pragma unroll
+    for (int q = 0; q < kNumInputs; ++q) x_in[q] = (q == IN_P_b || (q > IN_P_T && q != IN_T)) ? load_in(p, q, s) : 0.0;
+    const SampleConsts k = plume_sample_consts(x_in[IN_P_b], x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3],
+                                               x_in[IN_c4], x_in[IN_c5], p.torr);
+    double j_cex, base;
+    cex_terms(k.density, x_in[IN_sigma], x_in[IN_I_B0], p.radius0, j_cex, base);
+    BeamState b1, b2;
+    beam_init(b1, p.h, k.a1, __dmul_rn(base, k.amp1));
+    beam_init(b2, p.h, k.a2, __dmul_rn(base, k.amp2));
+    const int n_chunks = (A + kChunk - 1) / kChunk;
+
+    // plume.py:105-106: invalid samples return j_ion == 1e-20 at every angle -- that is what gets interpolated
+    bool invalid = (k.a1 <= 0.0);
+    if (!invalid && !(b1.amp >= 0.0 && b2.amp >= 0.0 && j_cex > 0.0)) {   // rare: look ahead for a non-positive j_ion
+        BeamState t1 = b1, t2 = b2;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int i0 = c * kChunk;
+            if (c != 0 && (c % kRestartChunks) == 0) {
+                beam_restart(t1, i0);
+                beam_restart(t2, i0);
+            }
+            double e1 = t1.amp * t1.ec, e2 = t2.amp * t2.ec, r1 = t1.rc, r2 = t2.rc;
+            for (int kk = 0; kk < kChunk && i0 + kk < A; ++kk) {
+                invalid |= ((e1 + e2) + j_cex <= 0.0);
+                e1 *= r1; r1 *= t1.q;
+                e2 *= r2; r2 *= t2.q;
+            }
+            beam_next_chunk(t1);
+            beam_next_chunk(t2);
+        }
+    }
+
+    double ll = 0.0, j_prev = 0.0;
+    double* pred = lp.y_pred ? lp.y_pred + s * (long long)lp.m : nullptr;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int i0 = c * kChunk;
+        if (c != 0 && (c % kRestartChunks) == 0) {
+            beam_restart(b1, i0);
+            beam_restart(b2, i0);
+        }
+        double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec, r1 = b1.rc, r2 = b2.rc;
+        const int kcount = min(kChunk, A - i0);
+        for (int kk = 0; kk < kcount; ++kk) {
+            const int i = i0 + kk;
+            const double j = invalid ? kInvalidFill : (e1 + e2) + j_cex;
+            if (i > 0) {
+                const double dj = j - j_prev;
+                for (int q = seg[i - 1]; q < seg[i]; ++q) {        // warp-uniform trip count, broadcast loads
+                    const MeasPoint mp = msm[q];
+                    const double yh = fma(mp.w, dj, j_prev);         // linear interpolation on [alpha[i-1], alpha[i]]
+                    const double r = (mp.y - yh) * mp.inv_sigma;
+                    ll = fma(-0.5 * r, r, ll);
+                    if (pred) pred[mp.orig] = yh;
+                }
+            }
+            j_prev = j;
+            e1 *= r1; r1 *= b1.q;
+            e2 *= r2; r2 *= b2.q;
+        }
+        beam_next_chunk(b1);
+        beam_next_chunk(b2);
+    }
+    if (lp.loglike) lp.loglike[s] = ll;
+}
+
 }  // namespace hpem

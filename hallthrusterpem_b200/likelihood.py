@@ -1,0 +1,65 @@
+"""Ion-current-density likelihood: the step right after the plume model in the reference's calibration scripts.
+
+`scripts/pem_v0/monte_carlo.py:265-270` mirrors the 0..90 deg sweep to (-90, 90) deg, interpolates it linearly
+(`scipy.interpolate.interp1d`) to the Faraday-probe angles, and `scripts/pem_v0/mcmc.py:103` sums
+`-0.5 * ((y - y_hat) / sigma)**2` over the probe points.  Here both happen inside one CUDA kernel (K3) that never
+materialises `j_ion`: per sample only the log-likelihood (and optionally the interpolated predictions) leave the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .engine import _Batch, get_grid, torr_2_pa
+
+
+class JionMeasurements:
+    """Probe angles (rad, |theta| <= pi/2), measured j_ion and standard deviations, resident on one device."""
+
+    def __init__(self, theta, y, sigma, n_angles: int = 91, sweep_radius: float = 1.0, device: int | None = None):
+        import torch
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.grid = get_grid(self.device, n_angles, np.atleast_1d(np.float64(sweep_radius)))
+        th, yy, sg = (np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1)) for v in (theta, y, sigma))
+        if not (th.shape == yy.shape == sg.shape):
+            raise ValueError('theta, y and sigma must have the same length')
+        if np.any(np.abs(th) > np.pi / 2):
+            raise ValueError('A value in x_new is outside the interpolation range.')     # what interp1d raises
+        self.m = int(th.shape[0])
+        dptr = ctypes.POINTER(ctypes.c_double)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.hpem_measurements_create(self.grid.handle, self.m, th.ctypes.data_as(dptr),
+                                                     yy.ctypes.data_as(dptr), sg.ctypes.data_as(dptr), ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.hpem_measurements_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def jion_log_likelihood(inputs: dict, meas: JionMeasurements, *, torr: float | None = None, return_pred: bool = False):
+    """Gaussian log-likelihood of the probe data under the plume model for every sample of `inputs`
+    (torch CUDA float64 tensors / scalars with the plume input names).  Returns a torch tensor of loop shape
+    (and the interpolated predictions, loop shape + (m,), with `return_pred`)."""
+    import torch
+    batch = _Batch(inputs, _lib.PLUME_INPUTS)
+    if not batch.on_device or batch.device_index != meas.device:
+        raise ValueError('jion_log_likelihood expects torch CUDA inputs on the device of the measurement set')
+    dev = f'cuda:{meas.device}'
+    ll = torch.empty(batch.out_shape, dtype=torch.float64, device=dev)
+    pred = torch.empty(batch.out_shape + (meas.m,), dtype=torch.float64, device=dev) if return_pred else None
+    stream = torch.cuda.current_stream(meas.device).cuda_stream
+    _lib.check(meas.lib.hpem_loglike(meas.grid.handle, meas._h, batch.n, ctypes.byref(batch.struct),
+                                     torr_2_pa() if torr is None else float(torr), ctypes.c_void_p(ll.data_ptr()),
+                                     ctypes.c_void_p(pred.data_ptr()) if return_pred else None, ctypes.c_void_p(stream)))
+    return (ll, pred) if return_pred else ll

@@ -184,6 +184,18 @@ int hpem_moments_accumulate_sampled(hpem_grid *grid, int64_t n, uint64_t seed, u
                                     const hpem_prior priors[HPEM_N_INPUTS], double torr_2_pa,
                                     const hpem_moments_spec *spec, double *sums, double *minmax, void *stream);
 
+/* ---- j_ion at measurement angles + Gaussian log-likelihood (the step after the path in the reference's calibration
+ * scripts: mirror to (-90, 90) deg + linear interp1d, scripts/pem_v0/monte_carlo.py:265-270; sum of
+ * -0.5 ((y - y_hat)/sigma)^2, scripts/pem_v0/mcmc.py:103).  Single radius, uniform grid.  j_ion is never materialised. */
+typedef struct hpem_measurements hpem_measurements; /* opaque: sorted / pre-weighted probe points on the device */
+/* theta[m] in radians, |theta| <= pi/2 (HPEM_ERR_INVALID_ARG otherwise, where interp1d raises); y[m], sigma[m] > 0: HOST arrays */
+int hpem_measurements_create(const hpem_grid *grid, int m, const double *theta, const double *y, const double *sigma,
+                             hpem_measurements **out);
+int hpem_measurements_destroy(hpem_measurements *meas);
+/* DEVICE buffers, asynchronous on `stream`: loglike (n) and/or y_pred (n, m) in the caller's point order (NULL = skip) */
+int hpem_loglike(const hpem_grid *grid, const hpem_measurements *meas, int64_t n, const hpem_inputs *in,
+                 double torr_2_pa, double *loglike, double *y_pred, void *stream);
+
 /* Number of kernel launches issued by this process through the library (for bench accounting). */
 int64_t hpem_launch_count(void);
 

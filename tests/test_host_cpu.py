@@ -88,7 +88,8 @@ def test_c_abi_library_exports_declared_symbols():
     declared = set(re.findall(r'^\s*(?:const\s+)?[A-Za-z_0-9]+\s*\*?\s*(hpem_[a-z_0-9]+)\s*\(', header, flags=re.M))
     assert {'hpem_abi_version', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',
             'hpem_eval', 'hpem_eval_host', 'hpem_launch_count', 'hpem_moments_layout_query',
-            'hpem_moments_accumulate', 'hpem_sample_inputs', 'hpem_moments_accumulate_sampled'} == declared
+            'hpem_moments_accumulate', 'hpem_sample_inputs', 'hpem_moments_accumulate_sampled',
+            'hpem_measurements_create', 'hpem_measurements_destroy', 'hpem_loglike'} == declared
     assert set(_lib.EXPORTED_SYMBOLS) == declared
     lib = ctypes.CDLL(str(path))
     for name in declared:
