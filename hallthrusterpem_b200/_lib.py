@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = (
     'hpem_eval', 'hpem_eval_host', 'hpem_launch_count',
     'hpem_moments_layout_query', 'hpem_moments_accumulate', 'hpem_sample_inputs', 'hpem_moments_accumulate_sampled',
     'hpem_measurements_create', 'hpem_measurements_destroy', 'hpem_loglike',
+    'hpem_basis_create', 'hpem_basis_destroy', 'hpem_compress', 'hpem_compress_field', 'hpem_reconstruct',
 )
 
 
@@ -159,6 +160,16 @@ def load() -> ctypes.CDLL:
         lib.hpem_measurements_destroy.restype = i32
         lib.hpem_loglike.argtypes = [vp, vp, i64, ctypes.POINTER(HpemInputs), dbl, vp, vp, vp]
         lib.hpem_loglike.restype = i32
+        lib.hpem_basis_create.argtypes = [i32, i32, i32, dptr, i32, ctypes.POINTER(vp)]
+        lib.hpem_basis_create.restype = i32
+        lib.hpem_basis_destroy.argtypes = [vp]
+        lib.hpem_basis_destroy.restype = i32
+        lib.hpem_compress.argtypes = [vp, vp, i64, ctypes.POINTER(HpemInputs), dbl, vp, vp]
+        lib.hpem_compress.restype = i32
+        lib.hpem_compress_field.argtypes = [vp, i64, vp, vp, vp]
+        lib.hpem_compress_field.restype = i32
+        lib.hpem_reconstruct.argtypes = [vp, i64, vp, vp, vp]
+        lib.hpem_reconstruct.restype = i32
         if lib.hpem_abi_version() != 1:
             raise HpemError(f'libhpem ABI version {lib.hpem_abi_version()} != 1')
         _lib = lib

@@ -15,6 +15,7 @@
 
 #include "../../include/hpem.h"
 #include "hpem_kernels.cuh"
+#include "hpem_compress.cuh"
 
 namespace {
 
@@ -792,6 +793,149 @@ int hpem_loglike(const hpem_grid* g, const hpem_measurements* meas, int64_t n, c
     if (rc != HPEM_OK) return rc;
     const unsigned blocks = (unsigned)((n + kThreadsL - 1) / kThreadsL);
     loglike_kernel<<<blocks, kThreadsL, smem, static_cast<cudaStream_t>(stream)>>>(p, lp);
+    HPEM_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return HPEM_OK;
+}
+
+}  // extern "C"
+
+// ---- SVD compression of the j_ion field (hpem_compress.cuh) ---------------------------------------------------------
+struct hpem_basis {
+    int device = 0;
+    int dof = 0, rank = 0, rank_pad = 0, norm_log10 = 1;
+    double* d_basis = nullptr;    // [dof][rank_pad]
+    double* d_basis_t = nullptr;  // [rank][dof]
+};
+
+namespace {
+hpem::BasisParams basis_params(const hpem_basis& b) {
+    hpem::BasisParams bp;
+    bp.dof = b.dof;
+    bp.rank = b.rank;
+    bp.rank_pad = b.rank_pad;
+    bp.norm_log10 = b.norm_log10;
+    bp.basis = b.d_basis;
+    bp.basis_t = b.d_basis_t;
+    return bp;
+}
+}  // namespace
+
+extern "C" {
+
+int hpem_basis_create(int device, int dof, int rank, const double* projection, int norm_log10, hpem_basis** out) {
+    if (!out) return fail(HPEM_ERR_INVALID_ARG, "out handle pointer is NULL");
+    *out = nullptr;
+    if (!projection) return fail(HPEM_ERR_INVALID_ARG, "projection matrix is NULL");
+    if (dof < 1 || dof > (1 << 20)) return fail(HPEM_ERR_INVALID_ARG, "dof must be in [1, 2^20], got %d", dof);
+    if (rank < 1 || rank > hpem::kMaxRank) return fail(HPEM_ERR_INVALID_ARG, "rank must be in [1, %d], got %d", hpem::kMaxRank, rank);
+    int ndev = 0;
+    HPEM_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(HPEM_ERR_INVALID_ARG, "device %d out of range (%d visible)", device, ndev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", device);
+    hpem_basis* b = new (std::nothrow) hpem_basis();
+    if (!b) return fail(HPEM_ERR_CUDA, "out of host memory");
+    b->device = device;
+    b->dof = dof;
+    b->rank = rank;
+    b->rank_pad = (rank + 3) / 4 * 4;
+    b->norm_log10 = norm_log10 ? 1 : 0;
+    std::vector<double> padded(size_t(dof) * b->rank_pad, 0.0), transposed(size_t(dof) * rank);
+    for (int i = 0; i < dof; ++i)
+        for (int k = 0; k < rank; ++k) {
+            padded[size_t(i) * b->rank_pad + k] = projection[size_t(i) * rank + k];
+            transposed[size_t(k) * dof + i] = projection[size_t(i) * rank + k];
+        }
+    cudaError_t e = cudaMalloc((void**)&b->d_basis, padded.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_basis_t, transposed.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(b->d_basis, padded.data(), padded.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(b->d_basis_t, transposed.data(), transposed.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        hpem_basis_destroy(b);
+        return fail(HPEM_ERR_CUDA, "projection upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = b;
+    return HPEM_OK;
+}
+
+int hpem_basis_destroy(hpem_basis* b) {
+    if (!b) return HPEM_OK;
+    DeviceGuard guard(b->device);
+    if (b->d_basis) cudaFree(b->d_basis);
+    if (b->d_basis_t) cudaFree(b->d_basis_t);
+    delete b;
+    return HPEM_OK;
+}
+
+int hpem_compress(const hpem_grid* g, const hpem_basis* b, int64_t n, const hpem_inputs* in, double torr_2_pa, double* latent,
+                  void* stream) {
+    if (!g || !b || !in || !latent) return fail(HPEM_ERR_INVALID_ARG, "NULL argument");
+    if (b->device != g->device) return fail(HPEM_ERR_INVALID_ARG, "basis and grid live on different devices");
+    if (g->n_radii != 1 || !g->uniform) return fail(HPEM_ERR_UNSUPPORTED, "fused compression needs one radius and the uniform grid");
+    if (b->dof != g->n_angles) return fail(HPEM_ERR_INVALID_ARG, "projection has %d rows, the grid has %d angles", b->dof, g->n_angles);
+    if (n < 0) return fail(HPEM_ERR_INVALID_ARG, "negative sample count");
+    if (n == 0) return HPEM_OK;
+    DeviceGuard guard(g->device);
+    if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", g->device);
+    using namespace hpem;
+    hpem_outputs no_out = {};
+    EvalParams p;
+    fill_params(*g, *in, no_out, 0, n, torr_2_pa, p);
+    const BasisParams bp = basis_params(*b);
+    const int rk = b->rank <= 4 ? 4 : b->rank <= 8 ? 8 : b->rank <= 16 ? 16 : 32;
+    const size_t smem = size_t(g->n_angles) * rk * sizeof(double);
+    const unsigned blocks = (unsigned)((n + kThreadsC - 1) / kThreadsC);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = HPEM_OK;
+#define HPEM_LAUNCH_LATENT(RK)                                              \
+    rc = set_smem(latent_kernel<RK>, smem);                                 \
+    if (rc != HPEM_OK) return rc;                                           \
+    latent_kernel<RK><<<blocks, kThreadsC, smem, st>>>(p, bp, latent)
+    switch (rk) {
+        case 4: HPEM_LAUNCH_LATENT(4); break;
+        case 8: HPEM_LAUNCH_LATENT(8); break;
+        case 16: HPEM_LAUNCH_LATENT(16); break;
+        default: HPEM_LAUNCH_LATENT(32); break;
+    }
+#undef HPEM_LAUNCH_LATENT
+    HPEM_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return HPEM_OK;
+}
+
+int hpem_compress_field(const hpem_basis* b, int64_t n, const double* field, double* latent, void* stream) {
+    if (!b || !field || !latent) return fail(HPEM_ERR_INVALID_ARG, "NULL argument");
+    if (n < 0) return fail(HPEM_ERR_INVALID_ARG, "negative sample count");
+    if (n == 0) return HPEM_OK;
+    DeviceGuard guard(b->device);
+    if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", b->device);
+    using namespace hpem;
+    const int rows_per_block = kThreadsC / 32;
+    const int64_t blocks = (n + rows_per_block - 1) / rows_per_block;
+    if (blocks > 2147483647LL) return fail(HPEM_ERR_INVALID_ARG, "too many rows for one call");
+    compress_field_kernel<<<(unsigned)blocks, kThreadsC, 0, static_cast<cudaStream_t>(stream)>>>(field, n, basis_params(*b), latent);
+    HPEM_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return HPEM_OK;
+}
+
+int hpem_reconstruct(const hpem_basis* b, int64_t n, const double* latent, double* field, void* stream) {
+    if (!b || !field || !latent) return fail(HPEM_ERR_INVALID_ARG, "NULL argument");
+    if (n < 0) return fail(HPEM_ERR_INVALID_ARG, "negative sample count");
+    if (n == 0) return HPEM_OK;
+    DeviceGuard guard(b->device);
+    if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", b->device);
+    using namespace hpem;
+    const size_t smem = size_t(b->dof) * b->rank * sizeof(double);
+    if (smem > 200 * 1024) return fail(HPEM_ERR_UNSUPPORTED, "projection matrix (%zu bytes) does not fit in shared memory", smem);
+    int rc = set_smem(reconstruct_kernel, smem);
+    if (rc != HPEM_OK) return rc;
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, b->device);
+    const int64_t total = n * (int64_t)b->dof;
+    const int64_t blocks = std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 8);
+    reconstruct_kernel<<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(latent, n, basis_params(*b), field);
     HPEM_CUDA(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return HPEM_OK;

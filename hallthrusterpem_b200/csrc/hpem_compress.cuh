@@ -1,0 +1,177 @@
+// hpem_compress.cuh -- SVD compression of the j_ion field quantity.
+//
+// Downstream of the plume model the reference never trains on the (n, A) field itself: amisc normalises j_ion with
+// log10 and projects every sample onto the leading left-singular vectors of a small "compression" sample set
+// (/root/reference/scripts/pem_v0/pem_v0_SPT-100.yml:272-280 `norm: log10`, `compression: {method: svd,
+// reconstruction_tol: 0.01}`; scripts/gen_data.py:279-290 builds the map with `var.normalize(...)` and
+// `var.compression.compute_map(...)`).  amisc itself is un-vendored (uv.lock:14-16, archermarx/amisc v0.8.1); the
+// arithmetic restated here is its published SVD compression: latent = U_r^T x, x = log10(j_ion); reconstruction
+// j_ion = 10^(U_r z).
+//
+// K4  latent_kernel        : fused plume model -> log10 -> projection.  One thread per sample runs the recurrence
+//                            sweep of K1u; j_ion is never materialised, only (n, rank) latent coefficients leave the SM.
+// K4f compress_field_kernel: projection of an already materialised (n, dof) field (one warp per row).
+// K5  reconstruct_kernel   : (n, rank) latent coefficients -> (n, dof) field, coalesced streaming stores.
+#pragma once
+#include "hpem_kernels.cuh"
+
+namespace hpem {
+
+constexpr int kMaxRank = 32;
+constexpr int kThreadsC = 128;
+
+struct BasisParams {
+    int dof;               // rows of the projection matrix (= n_angles for the fused kernel)
+    int rank;              // columns actually used
+    int rank_pad;          // row pitch of `basis` (multiple of 4, zero-padded)
+    int norm_log10;        // 1: x = log10(field) / field = 10^x ; 0: identity
+    const double* basis;   // device, [dof][rank_pad] row-major (projection_matrix, zero-padded columns)
+    const double* basis_t; // device, [rank][dof]  (transpose, for the reconstruction)
+};
+
+// plume.py:105 second term for the rare samples that can have a non-positive j_ion (negative amplitude or no CEX floor):
+// sweep once without storing anything.
+__device__ __forceinline__ bool lookahead_nonpositive(BeamState t1, BeamState t2, double j_cex, int A) {
+    bool any_bad = false;
+    const int n_chunks = (A + kChunk - 1) / kChunk;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int i0 = c * kChunk;
+        if (c != 0 && (c % kRestartChunks) == 0) {
+            beam_restart(t1, i0);
+            beam_restart(t2, i0);
+        }
+        double e1 = t1.amp * t1.ec, e2 = t2.amp * t2.ec, r1 = t1.rc, r2 = t2.rc;
+        for (int kk = 0; kk < kChunk && i0 + kk < A; ++kk) {
+            any_bad |= ((e1 + e2) + j_cex <= 0.0);
+            e1 *= r1; r1 *= t1.q;
+            e2 *= r2; r2 *= t2.q;
+        }
+        beam_next_chunk(t1);
+        beam_next_chunk(t2);
+    }
+    return any_bad;
+}
+
+// K4: RK = padded rank held in registers (4, 8, 16 or 32)
+template <int RK>
+__global__ void __launch_bounds__(kThreadsC) latent_kernel(const EvalParams p, const BasisParams bp, double* __restrict__ latent) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double* usm = reinterpret_cast<double*>(smem_raw);   // [A][RK]
+    const int A = p.n_angles;
+    for (int i = threadIdx.x; i < A * RK; i += kThreadsC) {
+        const int a = i / RK, k = i - a * RK;
+        usm[i] = (k < bp.rank_pad) ? bp.basis[a * bp.rank_pad + k] : 0.0;
+    }
+    __syncthreads();
+    const long long s = (long long)blockIdx.x * kThreadsC + threadIdx.x;
+    if (s >= p.n) return;
+
+    double x_in[kNumInputs];
+#pragma unroll
+    for (int q = 0; q < kNumInputs; ++q) x_in[q] = (q == IN_P_b || (q > IN_P_T && q != IN_T)) ? load_in(p, q, s) : 0.0;
+    const SampleConsts k = plume_sample_consts(x_in[IN_P_b], x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3],
+                                               x_in[IN_c4], x_in[IN_c5], p.torr);
+    double j_cex, base;
+    cex_terms(k.density, x_in[IN_sigma], x_in[IN_I_B0], p.radius0, j_cex, base);
+    BeamState b1, b2;
+    beam_init(b1, p.h, k.a1, __dmul_rn(base, k.amp1));
+    beam_init(b2, p.h, k.a2, __dmul_rn(base, k.amp2));
+
+    // plume.py:105-106: invalid samples return 1e-20 at every angle -- that row is what gets normalised and projected
+    bool invalid = (k.a1 <= 0.0);
+    if (!invalid && !(b1.amp >= 0.0 && b2.amp >= 0.0 && j_cex > 0.0)) invalid = lookahead_nonpositive(b1, b2, j_cex, A);
+
+    double z[RK];
+#pragma unroll
+    for (int r = 0; r < RK; ++r) z[r] = 0.0;
+    const int n_chunks = (A + kChunk - 1) / kChunk;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int i0 = c * kChunk;
+        if (c != 0 && (c % kRestartChunks) == 0) {
+            beam_restart(b1, i0);
+            beam_restart(b2, i0);
+        }
+        double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec, r1 = b1.rc, r2 = b2.rc;
+        const int kcount = min(kChunk, A - i0);
+        for (int kk = 0; kk < kcount; ++kk) {
+            const double j = invalid ? kInvalidFill : (e1 + e2) + j_cex;
+            const double x = bp.norm_log10 ? log10(j) : j;
+            const double2* u = reinterpret_cast<const double2*>(usm + (i0 + kk) * RK);   // broadcast loads
+#pragma unroll
+            for (int r = 0; r < RK; r += 2) {
+                const double2 uu = u[r >> 1];
+                z[r] = fma(uu.x, x, z[r]);
+                z[r + 1] = fma(uu.y, x, z[r + 1]);
+            }
+            e1 *= r1; r1 *= b1.q;
+            e2 *= r2; r2 *= b2.q;
+        }
+        beam_next_chunk(b1);
+        beam_next_chunk(b2);
+    }
+    double* out = latent + s * (long long)bp.rank;
+#pragma unroll
+    for (int r = 0; r < RK; ++r)
+        if (r < bp.rank) out[r] = z[r];
+}
+
+// K4f: one warp per row of a materialised field; lanes stride over the dof, warp-shuffle reduction per coefficient
+__global__ void __launch_bounds__(kThreadsC) compress_field_kernel(const double* __restrict__ field, long long n,
+                                                                   const BasisParams bp, double* __restrict__ latent) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (kThreadsC / 32) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const double* f = field + row * (long long)bp.dof;
+    for (int r0 = 0; r0 < bp.rank; r0 += 4) {          // four coefficients per pass over the row
+        double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+        for (int i = lane; i < bp.dof; i += 32) {
+            const double v = __ldg(f + i);
+            const double x = bp.norm_log10 ? log10(v) : v;
+            const double* u = bp.basis + (long long)i * bp.rank_pad + r0;   // rank_pad is a multiple of 4
+            z0 = fma(__ldg(u + 0), x, z0);
+            z1 = fma(__ldg(u + 1), x, z1);
+            z2 = fma(__ldg(u + 2), x, z2);
+            z3 = fma(__ldg(u + 3), x, z3);
+        }
+        z0 = warp_sum(z0); z1 = warp_sum(z1); z2 = warp_sum(z2); z3 = warp_sum(z3);
+        if (lane == 0) {
+            double* out = latent + row * (long long)bp.rank + r0;
+            out[0] = z0;
+            if (r0 + 1 < bp.rank) out[1] = z1;
+            if (r0 + 2 < bp.rank) out[2] = z2;
+            if (r0 + 3 < bp.rank) out[3] = z3;
+        }
+    }
+}
+
+// K5: flattened (sample, dof) index space, grid-stride; consecutive threads write consecutive addresses
+__global__ void __launch_bounds__(256) reconstruct_kernel(const double* __restrict__ latent, long long n, const BasisParams bp,
+                                                          double* __restrict__ field) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double* ut = reinterpret_cast<double*>(smem_raw);   // [rank][dof]
+    const int D = bp.dof, R = bp.rank;
+    for (int i = threadIdx.x; i < D * R; i += blockDim.x) ut[i] = bp.basis_t[i];
+    __syncthreads();
+    const long long total = n * (long long)D;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    long long s = idx / D;
+    int i = (int)(idx - s * D);
+    const long long ds = stride / D;
+    const int di = (int)(stride - ds * D);
+    for (; idx < total; idx += stride) {
+        const double* zr = latent + s * (long long)R;
+        double x = 0.0;
+        for (int r = 0; r < R; ++r) x = fma(ut[r * D + i], __ldg(zr + r), x);
+        __stcs(field + idx, bp.norm_log10 ? exp10(x) : x);
+        s += ds;
+        i += di;
+        if (i >= D) {
+            i -= D;
+            ++s;
+        }
+    }
+}
+
+}  // namespace hpem

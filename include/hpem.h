@@ -196,6 +196,23 @@ int hpem_measurements_destroy(hpem_measurements *meas);
 int hpem_loglike(const hpem_grid *grid, const hpem_measurements *meas, int64_t n, const hpem_inputs *in,
                  double torr_2_pa, double *loglike, double *y_pred, void *stream);
 
+/* ---- SVD compression of the j_ion field quantity (the data format downstream of the path: amisc normalises j_ion
+ * with log10 and keeps only its projection on the leading left-singular vectors of a compression sample set,
+ * scripts/pem_v0/pem_v0_SPT-100.yml:272-280, scripts/gen_data.py:279-290; amisc itself is un-vendored, uv.lock:14-16).
+ *   latent = U^T x,  x = log10(j_ion)  (norm_log10 = 1)  or  x = j_ion  (norm_log10 = 0);   j_ion = 10^(U z). */
+typedef struct hpem_basis hpem_basis; /* opaque: projection matrix U on the device */
+/* projection: HOST array (dof, rank) row-major = amisc's `SVD.projection_matrix`; 1 <= rank <= 32 */
+int hpem_basis_create(int device, int dof, int rank, const double *projection, int norm_log10, hpem_basis **out);
+int hpem_basis_destroy(hpem_basis *basis);
+/* Fused plume model + normalisation + projection: latent (n, rank) DEVICE; j_ion is never materialised.
+ * Needs dof == n_angles, one radius and the uniform grid.  Asynchronous on `stream`. */
+int hpem_compress(const hpem_grid *grid, const hpem_basis *basis, int64_t n, const hpem_inputs *in, double torr_2_pa,
+                  double *latent, void *stream);
+/* Projection of a materialised field (n, dof) DEVICE -> latent (n, rank) DEVICE. */
+int hpem_compress_field(const hpem_basis *basis, int64_t n, const double *field, double *latent, void *stream);
+/* latent (n, rank) DEVICE -> field (n, dof) DEVICE. */
+int hpem_reconstruct(const hpem_basis *basis, int64_t n, const double *latent, double *field, void *stream);
+
 /* Number of kernel launches issued by this process through the library (for bench accounting). */
 int64_t hpem_launch_count(void);
 

@@ -89,7 +89,8 @@ def test_c_abi_library_exports_declared_symbols():
     assert {'hpem_abi_version', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',
             'hpem_eval', 'hpem_eval_host', 'hpem_launch_count', 'hpem_moments_layout_query',
             'hpem_moments_accumulate', 'hpem_sample_inputs', 'hpem_moments_accumulate_sampled',
-            'hpem_measurements_create', 'hpem_measurements_destroy', 'hpem_loglike'} == declared
+            'hpem_measurements_create', 'hpem_measurements_destroy', 'hpem_loglike',
+            'hpem_basis_create', 'hpem_basis_destroy', 'hpem_compress', 'hpem_compress_field', 'hpem_reconstruct'} == declared
     assert set(_lib.EXPORTED_SYMBOLS) == declared
     lib = ctypes.CDLL(str(path))
     for name in declared:
@@ -231,3 +232,27 @@ def test_two_rank_merge_over_gloo_equals_single_rank():
     p = res.j_percentile([5, 50, 95])
     ref_p = np.percentile(o['j_ion'][:, layout.hist_angle_index], [5, 50, 95], axis=0)
     assert np.all(np.abs(p / ref_p - 1) < 0.3)          # 4 bins per octave -> <= 25 % bin width
+
+
+def test_pem_to_xarray_layout_matches_reference_text():
+    """data.py:239-279: (r, theta) field orientation, last-radius thrust, coords taken from j_ion_coords."""
+    from hallthrusterpem_b200.export import pem_to_xarray
+    n, A, R = 3, 7, 2
+    rng = np.random.default_rng(0)
+    alpha = np.linspace(0, np.pi / 2, A)
+    cell = np.empty((), dtype=object)
+    cell[()] = alpha
+    out = {'j_ion': rng.uniform(1, 2, (n, A, R)), 'j_ion_coords': np.broadcast_to(cell, (n,)), 'T_c': rng.uniform(0, 1, (n, R)),
+           'V_cc': rng.uniform(0, 50, n), 'T': rng.uniform(0, 1, n)}
+    ops = [{'P_b': 1e-5 * k} for k in range(n)]
+    entries = pem_to_xarray(ops, out, [1.0, 1.5])
+    assert len(entries) == n and entries[1]['operating_condition'] is ops[1]
+    f = entries[2]['data']['ion current density']
+    assert f['unit'] == 'A/m^2' and tuple(f['val'].dims) == ('r', 'theta')
+    assert np.array_equal(np.asarray(f['val'].values), out['j_ion'][2].T)
+    assert np.array_equal(np.asarray(f['val'].coords['theta']), alpha) and np.array_equal(np.asarray(f['val'].coords['r']), [1.0, 1.5])
+    assert float(np.asarray(entries[0]['data']['thrust']['val'].values)) == out['T_c'][0, -1]
+    assert float(np.asarray(entries[0]['data']['cathode coupling voltage']['val'].values)) == out['V_cc'][0]
+    single = pem_to_xarray(ops, {**out, 'j_ion': out['j_ion'][..., 0], 'T_c': out['T_c'][:, 0]}, 1.0, use_corrected_thrust=False)
+    assert np.asarray(single[0]['data']['ion current density']['val'].values).shape == (1, A)
+    assert float(np.asarray(single[1]['data']['thrust']['val'].values)) == out['T'][1]
