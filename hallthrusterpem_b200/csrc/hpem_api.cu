@@ -592,16 +592,26 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
     if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", g->device);
     using namespace hpem;
     const int n_chunks = (g->n_angles + kChunk - 1) / kChunk;
-    const size_t smem = size_t(g->n_angles_pad) * sizeof(double2) + size_t(kWarpsM) * 32 * kTilePitch * sizeof(double) +
-                        size_t(kWarpsM) * n_chunks * kChunk * 2 * sizeof(double) +
-                        size_t(lay.n_hist_angles) * lay.n_bins * sizeof(unsigned);
-    if (smem > 200 * 1024)
-        return fail(HPEM_ERR_UNSUPPORTED, "histogram/angle configuration needs %zu bytes of shared memory (> 200 KiB): "
-                    "raise hist_angle_stride or lower hist_sub_bits", smem);
-    rc = set_smem(moments_kernel, smem);
+    if (lay.n_bins > 65535) return fail(HPEM_ERR_UNSUPPORTED, "at most 65535 histogram bins per angle (got %d)", lay.n_bins);
+    // One persistent block per SM with as many warps as shared memory allows (per-warp tile + per-angle accumulators +
+    // histogram slot buffer; the block-wide histograms are paid once), several smaller blocks when few warps fit.
+    int dev_smem = 0;
+    HPEM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, g->device));
+    const size_t smem_budget = (size_t)dev_smem - 2048;   // static shared memory of the kernel + slack
+    int warps = kMaxWarpsM;
+    while (warps > 1 && moments_smem_bytes(g->n_angles_pad, n_chunks * kChunk, lay.n_hist_angles, lay.n_bins, warps) > smem_budget) --warps;
+    const size_t smem = moments_smem_bytes(g->n_angles_pad, n_chunks * kChunk, lay.n_hist_angles, lay.n_bins, warps);
+    if (smem > smem_budget)
+        return fail(HPEM_ERR_UNSUPPORTED, "histogram/angle configuration needs %zu bytes of shared memory (> %zu): "
+                    "raise hist_angle_stride or lower hist_sub_bits", smem, smem_budget);
+    rc = sampler ? set_smem(moments_kernel<true>, smem) : set_smem(moments_kernel<false>, smem);
     if (rc != HPEM_OK) return rc;
-    const int64_t batches = (n + kThreadsM - 1) / kThreadsM;
-    const int blocks = (int)std::min<int64_t>(batches, (int64_t)g->sm_count * 3);
+    const int threads = warps * 32;
+    int sm_smem = 0;
+    HPEM_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, g->device));
+    const int blocks_per_sm = std::max(1, std::min<int>({kMaxWarpsM / warps, (int)((size_t)sm_smem / (smem + 2048)), 4}));
+    const int64_t batches = (n + threads - 1) / threads;
+    const int blocks = (int)std::min<int64_t>(batches, (int64_t)g->sm_count * blocks_per_sm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Workspace& ws = g->ws;
     std::lock_guard<std::mutex> lock(ws.mu);
@@ -633,7 +643,10 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
     m.partial_minmax = ws.d_partial_minmax;
     SamplerParams sp_zero;
     std::memset(&sp_zero, 0, sizeof(sp_zero));
-    moments_kernel<<<blocks, kThreadsM, smem, st>>>(p, m, sampler ? *sampler : sp_zero);
+    if (sampler)
+        moments_kernel<true><<<blocks, threads, smem, st>>>(p, m, *sampler);
+    else
+        moments_kernel<false><<<blocks, threads, smem, st>>>(p, m, sp_zero);
     HPEM_CUDA(cudaGetLastError());
     const int fthreads = 256;
     moments_finalize_kernel<<<(unsigned)((lay.n_sums + fthreads - 1) / fthreads), fthreads, 0, st>>>(
@@ -653,6 +666,9 @@ static int fill_sampler(uint64_t seed, uint64_t first_index, const hpem_prior* p
         sp->prior[k].reserved = 0;
         sp->prior[k].a = q.a;
         sp->prior[k].b = q.b;
+        // LogUniform: exp(u (ln b - ln a) + ln a); the two logarithms are per-prior constants, taken once here
+        sp->prior[k].log_a = q.kind == HPEM_PRIOR_LOGUNIFORM ? std::log(q.a) : 0.0;
+        sp->prior[k].log_ratio = q.kind == HPEM_PRIOR_LOGUNIFORM ? std::log(q.b) - std::log(q.a) : 0.0;
     }
     sp->seed = seed;
     sp->first_index = first_index;
@@ -914,7 +930,12 @@ int hpem_compress_field(const hpem_basis* b, int64_t n, const double* field, dou
     const int rows_per_block = kThreadsC / 32;
     const int64_t blocks = (n + rows_per_block - 1) / rows_per_block;
     if (blocks > 2147483647LL) return fail(HPEM_ERR_INVALID_ARG, "too many rows for one call");
-    compress_field_kernel<<<(unsigned)blocks, kThreadsC, 0, static_cast<cudaStream_t>(stream)>>>(field, n, basis_params(*b), latent);
+    const BasisParams bp = basis_params(*b);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (b->rank <= 4) compress_field_kernel<4><<<(unsigned)blocks, kThreadsC, 0, st>>>(field, n, bp, latent);
+    else if (b->rank <= 8) compress_field_kernel<8><<<(unsigned)blocks, kThreadsC, 0, st>>>(field, n, bp, latent);
+    else if (b->rank <= 16) compress_field_kernel<16><<<(unsigned)blocks, kThreadsC, 0, st>>>(field, n, bp, latent);
+    else compress_field_kernel<32><<<(unsigned)blocks, kThreadsC, 0, st>>>(field, n, bp, latent);
     HPEM_CUDA(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return HPEM_OK;
@@ -927,15 +948,14 @@ int hpem_reconstruct(const hpem_basis* b, int64_t n, const double* latent, doubl
     DeviceGuard guard(b->device);
     if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", b->device);
     using namespace hpem;
-    const size_t smem = size_t(b->dof) * b->rank * sizeof(double);
-    if (smem > 200 * 1024) return fail(HPEM_ERR_UNSUPPORTED, "projection matrix (%zu bytes) does not fit in shared memory", smem);
-    int rc = set_smem(reconstruct_kernel, smem);
-    if (rc != HPEM_OK) return rc;
-    int sm_count = 148;
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, b->device);
-    const int64_t total = n * (int64_t)b->dof;
-    const int64_t blocks = std::min<int64_t>((total + 255) / 256, (int64_t)sm_count * 8);
-    reconstruct_kernel<<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(latent, n, basis_params(*b), field);
+    const int64_t blocks = (n + kReconSamples - 1) / kReconSamples;
+    if (blocks > 2147483647LL) return fail(HPEM_ERR_INVALID_ARG, "too many rows for one call");
+    const BasisParams bp = basis_params(*b);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (b->rank <= 4) reconstruct_kernel<4><<<(unsigned)blocks, kThreadsR, 0, st>>>(latent, n, bp, field);
+    else if (b->rank <= 8) reconstruct_kernel<8><<<(unsigned)blocks, kThreadsR, 0, st>>>(latent, n, bp, field);
+    else if (b->rank <= 16) reconstruct_kernel<16><<<(unsigned)blocks, kThreadsR, 0, st>>>(latent, n, bp, field);
+    else reconstruct_kernel<32><<<(unsigned)blocks, kThreadsR, 0, st>>>(latent, n, bp, field);
     HPEM_CUDA(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return HPEM_OK;

@@ -115,61 +115,68 @@ __global__ void __launch_bounds__(kThreadsC) latent_kernel(const EvalParams p, c
         if (r < bp.rank) out[r] = z[r];
 }
 
-// K4f: one warp per row of a materialised field; lanes stride over the dof, warp-shuffle reduction per coefficient
+// K4f: one warp per row of a materialised field.  Lane l takes elements l, l+32, ... (coalesced row reads, ONE log10 per
+// element), keeps RK partial coefficients in registers against the transposed projection [rank][dof] (coalesced,
+// L1-resident), and the warp reduces the RK partials by shuffles.
+template <int RK>
 __global__ void __launch_bounds__(kThreadsC) compress_field_kernel(const double* __restrict__ field, long long n,
                                                                    const BasisParams bp, double* __restrict__ latent) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (kThreadsC / 32) + (threadIdx.x >> 5);
     if (row >= n) return;
     const double* f = field + row * (long long)bp.dof;
-    for (int r0 = 0; r0 < bp.rank; r0 += 4) {          // four coefficients per pass over the row
-        double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
-        for (int i = lane; i < bp.dof; i += 32) {
-            const double v = __ldg(f + i);
-            const double x = bp.norm_log10 ? log10(v) : v;
-            const double* u = bp.basis + (long long)i * bp.rank_pad + r0;   // rank_pad is a multiple of 4
-            z0 = fma(__ldg(u + 0), x, z0);
-            z1 = fma(__ldg(u + 1), x, z1);
-            z2 = fma(__ldg(u + 2), x, z2);
-            z3 = fma(__ldg(u + 3), x, z3);
-        }
-        z0 = warp_sum(z0); z1 = warp_sum(z1); z2 = warp_sum(z2); z3 = warp_sum(z3);
-        if (lane == 0) {
-            double* out = latent + row * (long long)bp.rank + r0;
-            out[0] = z0;
-            if (r0 + 1 < bp.rank) out[1] = z1;
-            if (r0 + 2 < bp.rank) out[2] = z2;
-            if (r0 + 3 < bp.rank) out[3] = z3;
-        }
+    double z[RK];
+#pragma unroll
+    for (int r = 0; r < RK; ++r) z[r] = 0.0;
+    for (int i = lane; i < bp.dof; i += 32) {
+        const double v = __ldcs(f + i);
+        const double x = bp.norm_log10 ? log10(v) : v;
+        const double* u = bp.basis_t + i;
+#pragma unroll
+        for (int r = 0; r < RK; ++r)
+            if (r < bp.rank) z[r] = fma(__ldg(u + (long long)r * bp.dof), x, z[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < RK; ++r) z[r] = warp_sum(z[r]);
+    if (lane == 0) {
+        double* out = latent + row * (long long)bp.rank;
+#pragma unroll
+        for (int r = 0; r < RK; ++r)
+            if (r < bp.rank) out[r] = z[r];
     }
 }
 
-// K5: flattened (sample, dof) index space, grid-stride; consecutive threads write consecutive addresses
-__global__ void __launch_bounds__(256) reconstruct_kernel(const double* __restrict__ latent, long long n, const BasisParams bp,
-                                                          double* __restrict__ field) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    double* ut = reinterpret_cast<double*>(smem_raw);   // [rank][dof]
-    const int D = bp.dof, R = bp.rank;
-    for (int i = threadIdx.x; i < D * R; i += blockDim.x) ut[i] = bp.basis_t[i];
+// K5: a block takes kReconSamples consecutive samples; thread t owns field elements t, t+blockDim, ... with their
+// projection rows in registers and walks the block's samples, whose latent rows sit in shared memory (broadcast reads).
+// Consecutive threads write consecutive addresses of one row (coalesced streaming stores).
+constexpr int kReconSamples = 64;
+constexpr int kThreadsR = 128;
+template <int RK>
+__global__ void __launch_bounds__(kThreadsR) reconstruct_kernel(const double* __restrict__ latent, long long n, const BasisParams bp,
+                                                                double* __restrict__ field) {
+    __shared__ __align__(16) double zs[kReconSamples * RK];
+    const long long s0 = (long long)blockIdx.x * kReconSamples;
+    const int ns = (int)min((long long)kReconSamples, n - s0);
+    for (int e = threadIdx.x; e < ns * RK; e += kThreadsR) {
+        const int s = e / RK, r = e - s * RK;
+        zs[e] = (r < bp.rank) ? __ldg(latent + (s0 + s) * bp.rank + r) : 0.0;
+    }
     __syncthreads();
-    const long long total = n * (long long)D;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    long long s = idx / D;
-    int i = (int)(idx - s * D);
-    const long long ds = stride / D;
-    const int di = (int)(stride - ds * D);
-    for (; idx < total; idx += stride) {
-        const double* zr = latent + s * (long long)R;
-        double x = 0.0;
-        for (int r = 0; r < R; ++r) x = fma(ut[r * D + i], __ldg(zr + r), x);
-        __stcs(field + idx, bp.norm_log10 ? exp10(x) : x);
-        s += ds;
-        i += di;
-        if (i >= D) {
-            i -= D;
-            ++s;
+    for (int i = threadIdx.x; i < bp.dof; i += kThreadsR) {
+        double u[RK];
+#pragma unroll
+        for (int r = 0; r < RK; ++r) u[r] = (r < bp.rank) ? __ldg(bp.basis_t + (long long)r * bp.dof + i) : 0.0;
+        double* out = field + s0 * bp.dof + i;
+        for (int s = 0; s < ns; ++s) {
+            const double2* zr = reinterpret_cast<const double2*>(zs + s * RK);
+            double x = 0.0;
+#pragma unroll
+            for (int r = 0; r < RK; r += 2) {
+                const double2 zz = zr[r >> 1];
+                x = fma(u[r], zz.x, x);
+                x = fma(u[r + 1], zz.y, x);
+            }
+            __stcs(out + (long long)s * bp.dof, bp.norm_log10 ? exp10(x) : x);
         }
     }
 }

@@ -948,8 +948,21 @@ struct MomentsParams {
     double* partial_minmax;  // [gridDim.x][6]  (-min, max) x (V_cc, div_angle, T_c)
 };
 constexpr int kMomScalars = 12;  // n_samples n_invalid n_nonfinite_rows | {n_finite sum sumsq} x {V_cc div_angle T_c}
-constexpr int kThreadsM = 128;
-constexpr int kWarpsM = kThreadsM / 32;
+#ifndef HPEM_THREADS_M
+#define HPEM_THREADS_M 512
+#endif
+constexpr int kThreadsM = HPEM_THREADS_M;   // upper bound; the launch picks the warp count that fits shared memory
+constexpr int kMaxWarpsM = kThreadsM / 32;
+constexpr int kHbufPitch = 34;              // u16 bin indices, [32 samples][32 slots] + 2: row pitch of 17 words (odd)
+constexpr unsigned short kHbufSkip = 0xFFFFu;
+
+__host__ __device__ inline int moments_hist_pitch(int n_bins) { return n_bins | 1; }   // odd row pitch of the shared histograms
+// shared memory of one block with `warps` warps
+__host__ __device__ inline size_t moments_smem_bytes(int n_angles_pad, int a_pad, int n_hist_angles, int n_bins, int warps) {
+    return size_t(n_angles_pad) * sizeof(double2) + size_t(warps) * 32 * kTilePitch * sizeof(double) +
+           size_t(warps) * a_pad * 2 * sizeof(double) + size_t(n_hist_angles) * moments_hist_pitch(n_bins) * sizeof(unsigned) +
+           (n_hist_angles > 0 ? size_t(warps) * 32 * kHbufPitch * sizeof(unsigned short) : 0);
+}
 
 __device__ __forceinline__ int hist_bin(double j, const MomentsParams& m) {
     // log-linear bin: octave from the exponent field, 2^sub_bits linear sub-bins from the leading mantissa bits.
@@ -962,24 +975,48 @@ __device__ __forceinline__ int hist_bin(double j, const MomentsParams& m) {
     return min(max(b, 0), m.n_bins - 1);
 }
 
-__global__ void __launch_bounds__(kThreadsM, 3) moments_kernel(const EvalParams p, const MomentsParams m,
+// Histograms: a sample's bin index at every histogrammed angle is parked in a per-warp [32 samples][32 slots] u16 buffer
+// while the sweep runs; when 32 slots are full (or the sweep ends) lane a takes slot a and walks the 32 samples, so the
+// lanes of one warp never hit the same counter (different angles = different histogram rows, odd row pitch = different
+// banks).  The thread-per-sample alternative -- all 32 lanes incrementing the histogram of ONE angle -- serialises on
+// the few bins a population occupies at a given angle (measured: 44 % of the kernel at 1 histogram per 8 angles).
+__device__ __forceinline__ void hist_flush(unsigned* hist, const unsigned short* hbuf, int lane, int slot_base, int n_slots,
+                                           int pitch) {
+    __syncwarp();
+    if (lane < n_slots) {
+        unsigned* row = hist + (slot_base + lane) * pitch;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const unsigned short b = hbuf[r * kHbufPitch + lane];
+            if (b != kHbufSkip) atomicAdd(row + b, 1u);
+        }
+    }
+    __syncwarp();
+}
+
+template <bool SAMPLED>
+__global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams p, const MomentsParams m,
                                                                const __grid_constant__ SamplerParams sp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int A = p.n_angles;
     const int n_chunks = (A + kChunk - 1) / kChunk;
     const int a_pad = n_chunks * kChunk;
+    const int n_warps = blockDim.x >> 5;
+    const int hpitch = moments_hist_pitch(m.n_bins);
     double2* wsm = reinterpret_cast<double2*>(smem_raw);                               // [n_angles_pad]
     double* tiles = reinterpret_cast<double*>(wsm + p.n_angles_pad);                   // [warps][32][17]
-    double* acc_all = tiles + kWarpsM * 32 * kTilePitch;                               // [warps][a_pad][2]
-    unsigned* hist = reinterpret_cast<unsigned*>(acc_all + kWarpsM * a_pad * 2);       // [n_hist_angles][n_bins]
-    __shared__ double red[kWarpsM][kMomScalars + 6];
+    double* acc_all = tiles + n_warps * 32 * kTilePitch;                               // [warps][a_pad][2]
+    unsigned* hist = reinterpret_cast<unsigned*>(acc_all + n_warps * a_pad * 2);       // [n_hist_angles][hpitch]
+    unsigned short* hbuf_all = reinterpret_cast<unsigned short*>(hist + m.n_hist_angles * hpitch);   // [warps][32][34]
+    __shared__ double red[kMaxWarpsM][kMomScalars + 6];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* tile = tiles + warp * 32 * kTilePitch;
     double* acc = acc_all + warp * a_pad * 2;
-    for (int i = threadIdx.x; i < p.n_angles_pad; i += kThreadsM) wsm[i] = p.w[i];
-    for (int i = threadIdx.x; i < kWarpsM * a_pad * 2; i += kThreadsM) acc_all[i] = 0.0;
-    for (int i = threadIdx.x; i < m.n_hist_angles * m.n_bins; i += kThreadsM) hist[i] = 0u;
+    unsigned short* hbuf = hbuf_all + warp * 32 * kHbufPitch;
+    for (int i = threadIdx.x; i < p.n_angles_pad; i += blockDim.x) wsm[i] = p.w[i];
+    for (int i = threadIdx.x; i < n_warps * a_pad * 2; i += blockDim.x) acc_all[i] = 0.0;
+    for (int i = threadIdx.x; i < m.n_hist_angles * hpitch; i += blockDim.x) hist[i] = 0u;
     __syncthreads();
 
     double sc[kMomScalars];
@@ -989,15 +1026,18 @@ __global__ void __launch_bounds__(kThreadsM, 3) moments_kernel(const EvalParams 
     const bool want_cathode = m.want_cathode != 0;
     const bool want_thrust = p.has_thrust;
     const int col = lane & (kChunk - 1), half = lane >> 4;
+    const bool hist_any = m.hist_stride > 0;
+    const int h_stride = max(m.hist_stride, 1), h_shift = 20 - m.hist_sub_bits, h_last = m.n_bins - 1;
+    const int h_lo_key = ((m.hist_min_exp2 + 1023) << m.hist_sub_bits) - 1;
 
-    for (long long b0 = (long long)blockIdx.x * kThreadsM; b0 < p.n; b0 += (long long)gridDim.x * kThreadsM) {
+    for (long long b0 = (long long)blockIdx.x * blockDim.x; b0 < p.n; b0 += (long long)gridDim.x * blockDim.x) {
         const long long s_raw = b0 + threadIdx.x;
         const bool active = s_raw < p.n;
         const long long s = active ? s_raw : p.n - 1;
         if (b0 + warp * 32 >= p.n) continue;   // warp-uniform; no block-level barrier inside the loop
 
         double x_in[kNumInputs];
-        if (m.sampled) {
+        if (SAMPLED) {
             sample_inputs(sp, (unsigned long long)s, x_in);
         } else {
 #pragma unroll
@@ -1006,6 +1046,7 @@ __global__ void __launch_bounds__(kThreadsM, 3) moments_kernel(const EvalParams 
                 x_in[q] = needed ? load_in(p, q, s) : 0.0;
             }
         }
+        const double thrust = x_in[IN_T];
         if (want_cathode) {
             const double v = cathode_vcc(x_in[IN_P_b], x_in[IN_V_a], x_in[IN_T_e], x_in[IN_V_vac], x_in[IN_Pstar],
                                          x_in[IN_P_T], p.torr);
@@ -1052,7 +1093,6 @@ __global__ void __launch_bounds__(kThreadsM, 3) moments_kernel(const EvalParams 
             invalid = any_bad;
         }
         double num = 0.0, den = 0.0;
-        const bool hist_on = m.hist_stride > 0 && row_ok;
         if (!row_ok) {   // non-finite (or inactive shadow) row: contribute exact zeros to the per-angle sums, NaN to cos_div
             b1.amp = b2.amp = 0.0;
             b1.ec = b1.rc = b1.gc = b1.q = b1.qk = b1.hh = 1.0;
@@ -1062,6 +1102,9 @@ __global__ void __launch_bounds__(kThreadsM, 3) moments_kernel(const EvalParams 
         }
         const double j_fill = row_ok ? kInvalidFill : 0.0;
         double* my_row = tile + lane * kTilePitch;
+        // warps whose 32 rows are all ordinary (finite, valid) -- virtually all of them -- skip the per-element selects
+        const bool plain = !__any_sync(0xffffffffu, invalid || !row_ok);
+        int hslot = 0, hslot_base = 0;   // warp-uniform: filled slots of the histogram buffer, histogram row of slot 0
 
         for (int c = 0; c < n_chunks; ++c) {
             const int i0 = c * kChunk;
@@ -1071,34 +1114,60 @@ __global__ void __launch_bounds__(kThreadsM, 3) moments_kernel(const EvalParams 
             }
             double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec;
             double r1 = b1.rc, r2 = b2.rc;
+            if (plain) {
 #pragma unroll
-            for (int kk = 0; kk < kChunk; ++kk) {
-                const double2 w = wsm[i0 + kk];      // zero beyond A
-                const double sum = e1 + e2;
-                den = fma(w.x, sum, den);
-                num = fma(w.y, sum, num);
-                my_row[kk] = invalid ? j_fill : sum + j_cex;   // the value current_density() returns (columns >= A are never read back)
-                e1 *= r1; r1 *= b1.q;
-                e2 *= r2; r2 *= b2.q;
+                for (int kk = 0; kk < kChunk; ++kk) {
+                    const double2 w = wsm[i0 + kk];      // zero beyond A
+                    const double sum = e1 + e2;
+                    den = fma(w.x, sum, den);
+                    num = fma(w.y, sum, num);
+                    my_row[kk] = sum + j_cex;            // the value current_density() returns (columns >= A are never read back)
+                    e1 *= r1; r1 *= b1.q;
+                    e2 *= r2; r2 *= b2.q;
+                }
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < kChunk; ++kk) {
+                    const double2 w = wsm[i0 + kk];
+                    const double sum = e1 + e2;
+                    den = fma(w.x, sum, den);
+                    num = fma(w.y, sum, num);
+                    my_row[kk] = invalid ? j_fill : sum + j_cex;
+                    e1 *= r1; r1 *= b1.q;
+                    e2 *= r2; r2 *= b2.q;
+                }
             }
             beam_next_chunk(b1);
             beam_next_chunk(b2);
-            // histograms of the selected angles of this chunk (the angle is warp-uniform; one shared-memory atomic per sample)
-            if (hist_on) {
-                for (int i = (i0 + m.hist_stride - 1) & ~(m.hist_stride - 1); i < min(i0 + kChunk, A); i += m.hist_stride)
-                    atomicAdd(&hist[(i >> m.hist_shift) * m.n_bins + hist_bin(my_row[i - i0], m)], 1u);
+            // histogram bins of the selected angles of this chunk -> slot buffer (own row; the angle is warp-uniform)
+            if (hist_any) {
+                const int i_end = min(i0 + kChunk, A);
+                for (int i = (i0 + h_stride - 1) & ~(h_stride - 1); i < i_end; i += h_stride) {
+                    // log-linear bin from the leading bits of the fp64 pattern (see hist_bin)
+                    const int hi = __double2hiint(my_row[i - i0]);
+                    const int b = hi < 0 ? 0 : min(max((hi >> h_shift) - h_lo_key, 0), h_last);
+                    hbuf[lane * kHbufPitch + hslot] = row_ok ? (unsigned short)b : kHbufSkip;
+                    if (++hslot == 32) {
+                        hist_flush(hist, hbuf, lane, hslot_base, 32, hpitch);
+                        hslot_base += 32;
+                        hslot = 0;
+                    }
+                }
             }
             __syncwarp();
-            // column sums over the warp's 32 samples: 2 lanes per angle, 16 rows each
+            // column sums over the warp's 32 samples: 2 lanes per angle, 16 rows each (two independent chains per sum)
             {
-                double s1 = 0.0, s2 = 0.0;
+                double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
                 const double* tcol = tile + (half * 16) * kTilePitch + col;
 #pragma unroll
-                for (int rr = 0; rr < 16; ++rr) {
-                    const double v = tcol[rr * kTilePitch];
-                    s1 += v;
-                    s2 = fma(v, v, s2);
+                for (int rr = 0; rr < 16; rr += 2) {
+                    const double va = tcol[rr * kTilePitch], vb = tcol[(rr + 1) * kTilePitch];
+                    s1a += va;
+                    s1b += vb;
+                    s2a = fma(va, va, s2a);
+                    s2b = fma(vb, vb, s2b);
                 }
+                double s1 = s1a + s1b, s2 = s2a + s2b;
                 s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
                 s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
                 if (half == 0) {
@@ -1108,6 +1177,7 @@ __global__ void __launch_bounds__(kThreadsM, 3) moments_kernel(const EvalParams 
             }
             __syncwarp();
         }
+        if (hist_any && hslot > 0) hist_flush(hist, hbuf, lane, hslot_base, hslot, hpitch);
         double cd = num / den;
         if (cd == CUDART_INF) cd = CUDART_NAN;
         if (active) {
@@ -1120,7 +1190,7 @@ __global__ void __launch_bounds__(kThreadsM, 3) moments_kernel(const EvalParams 
                 mm[2] = fmax(mm[2], -dv); mm[3] = fmax(mm[3], dv);
             }
             if (want_thrust) {
-                const double tc = __dmul_rn(x_in[IN_T], cd);
+                const double tc = __dmul_rn(thrust, cd);
                 if (tc == tc) {
                     sc[9] += 1.0; sc[10] += tc; sc[11] = fma(tc, tc, sc[11]);
                     mm[4] = fmax(mm[4], -tc); mm[5] = fmax(mm[5], tc);
@@ -1147,23 +1217,26 @@ __global__ void __launch_bounds__(kThreadsM, 3) moments_kernel(const EvalParams 
     double* out = m.partials + (long long)blockIdx.x * m.n_sums;
     if (threadIdx.x < kMomScalars) {
         double v = 0.0;
-        for (int w = 0; w < kWarpsM; ++w) v += red[w][threadIdx.x];
+        for (int w = 0; w < n_warps; ++w) v += red[w][threadIdx.x];
         out[threadIdx.x] = v;
     } else if (threadIdx.x < kMomScalars + 6) {
         double v = -CUDART_INF;
-        for (int w = 0; w < kWarpsM; ++w) v = fmax(v, red[w][threadIdx.x]);
+        for (int w = 0; w < n_warps; ++w) v = fmax(v, red[w][threadIdx.x]);
         m.partial_minmax[(long long)blockIdx.x * 6 + (threadIdx.x - kMomScalars)] = v;
     }
-    for (int i = threadIdx.x; i < A; i += kThreadsM) {
+    for (int i = threadIdx.x; i < A; i += blockDim.x) {
         double s1 = 0.0, s2 = 0.0;
-        for (int w = 0; w < kWarpsM; ++w) {
+        for (int w = 0; w < n_warps; ++w) {
             s1 += acc_all[(w * a_pad + i) * 2 + 0];
             s2 += acc_all[(w * a_pad + i) * 2 + 1];
         }
         out[m.off_angle_sum + i] = s1;
         out[m.off_angle_sumsq + i] = s2;
     }
-    for (int i = threadIdx.x; i < m.n_hist_angles * m.n_bins; i += kThreadsM) out[m.off_hist + i] = double(hist[i]);
+    for (int i = threadIdx.x; i < m.n_hist_angles * m.n_bins; i += blockDim.x) {
+        const int a = i / m.n_bins, b = i - a * m.n_bins;
+        out[m.off_hist + i] = double(hist[a * hpitch + b]);
+    }
 }
 
 // sums[i] += sum over blocks (fixed order) of partials[b][i];  minmax[i] = max(minmax[i], max_b partial_minmax[b][i])

@@ -14,10 +14,11 @@ namespace hpem {
 
 enum PriorKind { PRIOR_CONST = 0, PRIOR_UNIFORM = 1, PRIOR_LOGUNIFORM = 2, PRIOR_NORMAL = 3 };
 
-struct Prior {      // mirrors struct hpem_prior
+struct Prior {      // struct hpem_prior + host-precomputed constants
     int32_t kind;
     int32_t reserved;
     double a, b;    // const: a | uniform: [a, b) | loguniform: [a, b) in the variable itself | normal: mean a, std b
+    double log_a, log_ratio;   // loguniform: ln a, ln b - ln a (host std::log)
 };
 
 struct SamplerParams {
@@ -57,7 +58,7 @@ __device__ __forceinline__ double apply_prior(const Prior& pr, double u, unsigne
                                               uint32_t input) {
     switch (pr.kind) {
         case PRIOR_UNIFORM: return fma(u, pr.b - pr.a, pr.a);
-        case PRIOR_LOGUNIFORM: return exp(fma(u, log(pr.b) - log(pr.a), log(pr.a)));
+        case PRIOR_LOGUNIFORM: return exp(fma(u, pr.log_ratio, pr.log_a));
         case PRIOR_NORMAL: {   // Box-Muller with a second uniform from stream 1 of the same (sample, input)
             double v0, v1;
             uniform_pair(seed, sample, input, 1u, v0, v1);
