@@ -30,6 +30,7 @@ FLAG_FORCE_DIRECT = 1
 FLAG_NO_TMA = 2
 FLAG_LANES1 = 4
 FLAG_LANES4 = 8
+FLAG_NO_QUAD = 16
 
 EXPORTED_SYMBOLS = (
     'hpem_abi_version', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',

@@ -82,7 +82,7 @@ struct hpem_grid {
     double* d_alpha = nullptr;
     double* d_radii = nullptr;
     std::vector<double> alpha_host;
-    size_t smem_tma = 0, smem_stg = 0, smem_nostore = 0, smem_rows = 0;  // dynamic shared memory of the K1u variants
+    size_t smem_tma = 0, smem_tma1 = 0, smem_quad = 0, smem_quad1 = 0, smem_stg = 0, smem_nostore = 0, smem_rows = 0;  // dynamic shared memory of the K1u variants
     size_t smem_v_store = 0, smem_v_nostore = 0;          // ... and of K1v
     int sm_count = 148;
     bool smem_ok = false;
@@ -157,42 +157,60 @@ EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// Tensor map of j_ion viewed as (rows = samples, cols = angles); box = box_rows samples x box_cols angles.
-int make_j_map(double* j_ion, int n_angles, long long n_rows, int box_cols, int box_rows, bool swizzle128,
+// Tensor map of j_ion viewed as (rows, cols): `n_cols` columns per row, rows `row_pitch` elements apart;
+// box = box_rows x box_cols.  (n, A) view: n_cols = row_pitch = A.  Quad-row view (A % 4 != 0): see kStoreQuad.
+int make_j_map(double* base, long long n_cols, long long n_rows, long long row_pitch, int box_cols, int box_rows, bool swizzle128,
                CUtensorMap* map) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(HPEM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    const cuuint64_t dims[2] = {(cuuint64_t)n_angles, (cuuint64_t)n_rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)n_angles * sizeof(double)};
+    const cuuint64_t dims[2] = {(cuuint64_t)n_cols, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)row_pitch * sizeof(double)};
     const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, j_ion, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HPEM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return HPEM_OK;
 }
 
-// 3-D view of j_ion for K1u: (16 angles inside a 128-byte column block, samples, column blocks); one box = kTmaCB
-// column blocks x 32 samples x 16 angles, read from [column block][sample][128 B] sub-tiles (128B swizzle).
-int make_j_map3(double* j_ion, int n_angles, long long n_rows, CUtensorMap* map) {
+// 3-D view for K1u: (16 angles inside a 128-byte column block, rows, column blocks); one box = kTmaCB column blocks x
+// box_rows rows x 16 angles, read from [column block][row][128 B] sub-tiles (128B swizzle).
+int make_j_map3(double* base, long long n_cols, long long n_rows, long long row_pitch, int box_rows, CUtensorMap* map) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(HPEM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    const int n_blocks = n_angles / hpem::kChunk;
+    const long long n_blocks = n_cols / hpem::kChunk;
     if (n_blocks < hpem::kTmaCB) {   // never used by the kernel (every group takes the 2-D path)
         std::memset(map, 0, sizeof(*map));
         return HPEM_OK;
     }
-    // dimension order (angle within block, sample, column block): the box is laid out in shared memory with the FIRST
-    // dimension fastest, i.e. [column block][sample][16 angles] -- one 128B-swizzled 32x16 sub-tile per column block
+    // dimension order (angle within block, row, column block): the box is laid out in shared memory with the FIRST
+    // dimension fastest, i.e. [column block][row][16 angles] -- one 128B-swizzled sub-tile per column block
     const cuuint64_t dims[3] = {(cuuint64_t)hpem::kChunk, (cuuint64_t)n_rows, (cuuint64_t)n_blocks};
-    const cuuint64_t strides[2] = {(cuuint64_t)n_angles * sizeof(double), (cuuint64_t)hpem::kChunk * sizeof(double)};
-    const cuuint32_t box[3] = {(cuuint32_t)hpem::kChunk, 32u, (cuuint32_t)hpem::kTmaCB};
+    const cuuint64_t strides[2] = {(cuuint64_t)row_pitch * sizeof(double), (cuuint64_t)hpem::kChunk * sizeof(double)};
+    const cuuint32_t box[3] = {(cuuint32_t)hpem::kChunk, (cuuint32_t)box_rows, (cuuint32_t)hpem::kTmaCB};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, j_ion, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HPEM_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
     return HPEM_OK;
+}
+
+// Row phases of the quad-row store mode (see kStoreQuad): for a 32-byte aligned base, row r starts (r A 8) mod 32 bytes
+// into a sector; lead = elements up to the next sector boundary, body = common sector-aligned length, tail = the rest.
+struct QuadLayout {
+    int lead[4], tail[4], body;
+};
+QuadLayout quad_layout(int n_angles) {
+    QuadLayout q;
+    q.body = 1 << 30;
+    for (int f = 0; f < 4; ++f) {
+        q.lead[f] = (4 - (int)(((long long)f * n_angles) % 4)) % 4;
+        q.body = std::min(q.body, (n_angles - q.lead[f]) & ~3);
+    }
+    q.body = std::max(q.body, 0);
+    for (int f = 0; f < 4; ++f) q.tail[f] = n_angles - q.lead[f] - q.body;
+    return q;
 }
 
 int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store_j, uint32_t flags, cudaStream_t st) {
@@ -211,7 +229,7 @@ int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store
         CUtensorMap map;
         std::memset(&map, 0, sizeof(map));
         if (tma_ok) {
-            int rc = make_j_map(p.j_ion, (int)row_len, p.n, kChunk, 32, true, &map);
+            int rc = make_j_map(p.j_ion, row_len, p.n, row_len, kChunk, 32, true, &map);
             if (rc != HPEM_OK) return rc;
             const size_t smem = wbytes + rad_bytes + size_t(kWarpsU) * kTmaBuffers * kTmaTileBytes;
             rc = set_smem(eval_multi_radius_kernel<true>, smem);
@@ -225,35 +243,62 @@ int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store
         }
     } else if (use_uniform || !plume) {
         const unsigned blocks = (unsigned)((p.n + kThreadsU - 1) / kThreadsU);
-        CUtensorMap map, map3;
-        std::memset(&map, 0, sizeof(map));
-        std::memset(&map3, 0, sizeof(map3));
-        // TMA tensor stores need 16-byte aligned rows: even angle count and a 16-byte aligned base
-        const bool tma_ok = store_j && (g.n_angles % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.j_ion) & 15u) == 0) &&
+        JMaps maps;
+        std::memset(&maps, 0, sizeof(maps));
+        const int A = g.n_angles;
+        // TMA tensor stores over the (n, A) view need sector-aligned rows (A % 4 == 0; 16-byte alignment alone -- A % 2 == 0
+        // -- works but writes partial sectors: 4.4 instead of 5.6 TB/s) and an aligned base ...
+        const bool tma_ok = store_j && (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.j_ion) & 15u) == 0) &&
                             !(flags & HPEM_FLAG_NO_TMA);
-        // default choice (measured on B200, tools/variant_sweep.py): TMA tensor stores need even A, and with them the
-        // one-lane sweep (K1u) is the faster kernel; for odd A the four-lane sweep with whole-row bulk stores (K1v) wins
-        // K1u whole-row mode pays off while the warp's 32 x A tile is small (<= 16 KB, A <= 63: 0.123 ms vs 0.163 ms for
-        // K1v at A = 51); at A = 91 the 23 KB tile leaves 8 warps per SM and K1v is faster (0.204 ms vs 0.220 ms)
-        const bool rows_fit = (g.n_angles % 2 == 1) && size_t(32) * g.n_angles * 8 <= 16 * 1024;
+        // ... every other angle count (the reference's 91 included) takes the quad-row view: four rows span whole sectors.
+        // Needs a sample count that is a multiple of 4 (launch_range() peels the remainder off) and a 32-byte aligned base.
+        QuadLayout ql = quad_layout(A);
+        const bool rows_fit = (A % 2 == 1) && size_t(32) * A * 8 <= 16 * 1024;   // small odd A: whole-row mode (0.123 vs 0.142 ms at A = 51)
+        // (below 64 angles the lead/tail elements of the quad-row mode cost more than the partial sectors they avoid)
+        const bool quad_ok = store_j && (A % 4 != 0) && A >= kQuadMinAngles && ql.body >= kChunk && ((reinterpret_cast<uintptr_t>(p.j_ion) & 31u) == 0) &&
+                             (p.n % 4 == 0) && !(flags & (HPEM_FLAG_NO_TMA | HPEM_FLAG_NO_QUAD)) && 4LL * A < 2147483647LL;
+        // fallbacks without tensor stores: even A through 16-byte aligned (n, A) boxes, small odd A through K1u's whole-row
+        // mode (32 x A tile <= 16 KB), larger odd A through the four-lane sweep with whole-row bulk stores (K1v)
+        const bool tma16_ok = store_j && (A % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.j_ion) & 15u) == 0) && !(flags & HPEM_FLAG_NO_TMA);
         const bool lanes1 = (flags & HPEM_FLAG_LANES1) ? true : (flags & HPEM_FLAG_LANES4) ? false
-                                                                 : (g.n_angles % 2 == 0 || rows_fit);
+                                                                 : (A % 2 == 0 || rows_fit || quad_ok);
+        // one staging buffer per warp (twice the resident warps) while the per-sample prologue dominates: measured cross-over
+        // at ~160 angles for the (n, A) boxes and ~200 for the quad-row mode (tools/variant_angles.py)
+        const bool one_buf = A <= (quad_ok ? kOneBufferMaxAnglesQuad : kOneBufferMaxAngles);
         if (!plume) {
-            eval_uniform_kernel<false, false, kStoreStg><<<blocks, kThreadsU, 0, st>>>(p, map, map3);
-        } else if (lanes1) {   // K1u: one lane per sample for the angle sweep as well (128-byte row pieces)
+            eval_uniform_kernel<false, false, kStoreStg, 2><<<blocks, kThreadsU, 0, st>>>(p, maps);
+        } else if (lanes1) {   // K1u: one lane per sample for the angle sweep as well
             if (!store_j) {
-                eval_uniform_kernel<true, false, kStoreStg><<<blocks, kThreadsU, g.smem_nostore, st>>>(p, map, map3);
-            } else if (tma_ok) {
-                int rc = make_j_map(p.j_ion, g.n_angles, p.n, kChunk, 32, true, &map);
-                if (rc == HPEM_OK) rc = make_j_map3(p.j_ion, g.n_angles, p.n, &map3);
+                eval_uniform_kernel<true, false, kStoreStg, 2><<<blocks, kThreadsU, g.smem_nostore, st>>>(p, maps);
+            } else if (quad_ok) {
+                hpem::EvalParams pq = p;
+                pq.q_body = ql.body;
+                for (int f = 0; f < 4; ++f) {
+                    pq.q_lead[f] = ql.lead[f];
+                    pq.q_tail[f] = ql.tail[f];
+                    double* base = p.j_ion + (long long)f * A + ql.lead[f];    // first body element of phase f: 32-byte aligned
+                    int rc = make_j_map(base, ql.body, p.n / 4, 4LL * A, kChunk, 8, true, &maps.m2[f]);
+                    if (rc == HPEM_OK) rc = make_j_map3(base, ql.body, p.n / 4, 4LL * A, 8, &maps.m3[f]);
+                    if (rc != HPEM_OK) return rc;
+                }
+                if (one_buf)
+                    eval_uniform_kernel<true, true, kStoreQuad, 1><<<blocks, kThreadsU, g.smem_quad1, st>>>(pq, maps);
+                else
+                    eval_uniform_kernel<true, true, kStoreQuad, 2><<<blocks, kThreadsU, g.smem_quad, st>>>(pq, maps);
+            } else if (tma_ok || tma16_ok) {
+                int rc = make_j_map(p.j_ion, A, p.n, A, kChunk, 32, true, &maps.m2[0]);
+                if (rc == HPEM_OK) rc = make_j_map3(p.j_ion, A, p.n, A, 32, &maps.m3[0]);
                 if (rc != HPEM_OK) return rc;
-                eval_uniform_kernel<true, true, kStoreTma><<<blocks, kThreadsU, g.smem_tma, st>>>(p, map, map3);
+                if (one_buf)
+                    eval_uniform_kernel<true, true, kStoreTma, 1><<<blocks, kThreadsU, g.smem_tma1, st>>>(p, maps);
+                else
+                    eval_uniform_kernel<true, true, kStoreTma, 2><<<blocks, kThreadsU, g.smem_tma, st>>>(p, maps);
             } else if (rows_fit && !(flags & HPEM_FLAG_NO_TMA)) {   // small odd A: whole rows, one 1-D bulk store per warp
                 hpem::EvalParams pr = p;
                 pr.bulk_ok = (reinterpret_cast<uintptr_t>(p.j_ion) & 15u) == 0;
-                eval_uniform_kernel<true, true, kStoreRows><<<blocks, kThreadsU, g.smem_rows, st>>>(pr, map, map3);
+                eval_uniform_kernel<true, true, kStoreRows, 2><<<blocks, kThreadsU, g.smem_rows, st>>>(pr, maps);
             } else {
-                eval_uniform_kernel<true, true, kStoreStg><<<blocks, kThreadsU, g.smem_stg, st>>>(p, map, map3);
+                eval_uniform_kernel<true, true, kStoreStg, 2><<<blocks, kThreadsU, g.smem_stg, st>>>(p, maps);
             }
         } else {               // K1v: four lanes per sample in the sweep, whole rows per bulk store
             const unsigned vblocks = (unsigned)((p.n + kThreadsV - 1) / kThreadsV);
@@ -271,6 +316,25 @@ int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store
     g_launches.fetch_add(1, std::memory_order_relaxed);
     HPEM_CUDA(cudaGetLastError());
     return HPEM_OK;
+}
+
+// fill_params + launch for samples [first, first + count).  The quad-row store mode needs a sample count that is a
+// multiple of 4: other ranges are split into that part and the last 1-3 samples (which take a fallback store mode).
+int launch_range(const hpem_grid& g, const hpem_inputs& in, const hpem_outputs& out, int64_t first, int64_t count, double torr,
+                 bool plume, uint32_t flags, cudaStream_t st) {
+    const bool store_j = out.j_ion != nullptr;
+    const bool quad_candidate = plume && store_j && g.uniform && g.n_radii == 1 && g.smem_ok && (g.n_angles % 4 != 0) &&
+                                quad_layout(g.n_angles).body >= hpem::kChunk &&
+                                g.n_angles >= hpem::kQuadMinAngles &&
+                                !(flags & (HPEM_FLAG_FORCE_DIRECT | HPEM_FLAG_NO_TMA | HPEM_FLAG_NO_QUAD | HPEM_FLAG_LANES4));
+    if (quad_candidate && (count & 3) && count > 4) {
+        int rc = launch_range(g, in, out, first, count & ~(int64_t)3, torr, plume, flags, st);
+        if (rc != HPEM_OK) return rc;
+        return launch_range(g, in, out, first + (count & ~(int64_t)3), count & 3, torr, plume, flags, st);
+    }
+    hpem::EvalParams p;
+    fill_params(g, in, out, first, count, torr, p);
+    return launch(g, p, plume, store_j, flags, st);
 }
 
 int check_request(const hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_outputs* out) {
@@ -359,18 +423,24 @@ int hpem_grid_create(int device, int n_angles, const double* alpha, const double
     const size_t wbytes = size_t(g->n_angles_pad) * sizeof(double2) + 1024;  // + slack for the 1024-byte alignment
     g->smem_nostore = wbytes;
     g->smem_stg = wbytes + size_t(hpem::kWarpsU) * 32 * hpem::kTilePitch * sizeof(double);
-    g->smem_tma = wbytes + size_t(hpem::kWarpsU) * hpem::kTmaBuffers * hpem::kTmaGroupBytes;
+    g->smem_tma = wbytes + size_t(hpem::kWarpsU) * 2 * hpem::kTmaGroupBytes;
+    g->smem_tma1 = wbytes + size_t(hpem::kWarpsU) * 1 * hpem::kTmaGroupBytes;
+    g->smem_quad = g->smem_tma + size_t(hpem::kWarpsU) * hpem::kBsecBytes;
+    g->smem_quad1 = g->smem_tma1 + size_t(hpem::kWarpsU) * hpem::kBsecBytes;
     g->smem_rows = wbytes + size_t(hpem::kWarpsU) * ((size_t(32) * n_angles * 8 + 15) & ~size_t(15));
     const size_t xbytes = size_t(hpem::kWarpsV) * 32 * hpem::kXchPitch * sizeof(double);
     g->smem_v_nostore = wbytes + xbytes;
     g->smem_v_store = wbytes + xbytes + size_t(hpem::kWarpsV) * hpem::k1v_tile_bytes(n_angles);
     g->smem_ok = std::max(std::max(g->smem_stg, g->smem_tma), g->smem_v_store) <= 200 * 1024;
     if (g->smem_ok) {
-        int rc = set_smem(hpem::eval_uniform_kernel<true, true, hpem::kStoreTma>, g->smem_tma);
-        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, true, hpem::kStoreStg>, g->smem_stg);
+        int rc = set_smem(hpem::eval_uniform_kernel<true, true, hpem::kStoreTma, 2>, g->smem_tma);
+        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, true, hpem::kStoreTma, 1>, g->smem_tma1);
+        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, true, hpem::kStoreQuad, 2>, g->smem_quad);
+        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, true, hpem::kStoreQuad, 1>, g->smem_quad1);
+        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, true, hpem::kStoreStg, 2>, g->smem_stg);
         if (rc == HPEM_OK && g->smem_rows <= 200 * 1024)
-            rc = set_smem(hpem::eval_uniform_kernel<true, true, hpem::kStoreRows>, g->smem_rows);
-        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, false, hpem::kStoreStg>, g->smem_nostore);
+            rc = set_smem(hpem::eval_uniform_kernel<true, true, hpem::kStoreRows, 2>, g->smem_rows);
+        if (rc == HPEM_OK) rc = set_smem(hpem::eval_uniform_kernel<true, false, hpem::kStoreStg, 2>, g->smem_nostore);
         if (rc == HPEM_OK) rc = set_smem(hpem::eval_lanes4_kernel<true>, g->smem_v_store);
         if (rc == HPEM_OK) rc = set_smem(hpem::eval_lanes4_kernel<false>, g->smem_v_nostore);
         if (rc != HPEM_OK) return cleanup(rc);
@@ -418,9 +488,7 @@ int hpem_eval(const hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_o
     const int64_t max_per_launch = (int64_t)1 << 30;
     for (int64_t first = 0; first < n; first += max_per_launch) {
         const int64_t count = std::min(max_per_launch, n - first);
-        hpem::EvalParams p;
-        fill_params(*g, *in, *out, first, count, torr_2_pa, p);
-        rc = launch(*g, p, plume, out->j_ion != nullptr, flags, st);
+        rc = launch_range(*g, *in, *out, first, count, torr_2_pa, plume, flags, st);
         if (rc != HPEM_OK) return rc;
     }
     return HPEM_OK;
@@ -522,9 +590,7 @@ int hpem_eval_host(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_ou
         for (int64_t c = 0; c < n_chunks; ++c) {
             const int64_t first = c * chunk, count = std::min(chunk, nb - first);
             if (c % 8 == 0) HPEM_CUDA(cudaStreamWaitEvent(ws.s_compute, ws.h2d_events[c / 8], 0));
-            hpem::EvalParams p;
-            fill_params(*g, din, dout, first, count, torr_2_pa, p);
-            rc = launch(*g, p, plume, dout.j_ion != nullptr, flags, ws.s_compute);
+            rc = launch_range(*g, din, dout, first, count, torr_2_pa, plume, flags, ws.s_compute);
             if (rc != HPEM_OK) return rc;
             if (out->j_ion) {
                 HPEM_CUDA(cudaEventRecord(ws.events[c], ws.s_compute));

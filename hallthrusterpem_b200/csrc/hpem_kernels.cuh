@@ -54,6 +54,14 @@ struct EvalParams {
     double radius0;          // radii[0]
     bool has_thrust;         // input T supplied
     bool bulk_ok;            // j_ion base is 16-byte aligned and bulk (TMA) stores are allowed
+    // quad-row store mode (kStoreQuad): per row phase (sample index mod 4) the elements before the first / after the last
+    // 32-byte-aligned body element, and the common body length (multiple of 4)
+    int q_lead[4], q_tail[4], q_body;
+};
+
+struct JMaps {               // tensor maps of j_ion: [0] the (n, A) view; quad-row mode: one pair per row phase
+    CUtensorMap m2[4];       // 2-D, box = 16 columns x rows (clips ragged columns)
+    CUtensorMap m3[4];       // 3-D (16 angles, rows, column blocks), box = kTmaCB column blocks
 };
 
 constexpr int kChunk = 16;          // angles per staged tile / inner recurrence length
@@ -118,6 +126,12 @@ constexpr int kTmaBuffers = HPEM_TMA_BUFFERS;
 #endif
 constexpr int kTmaCB = HPEM_TMA_CB;   // K1u: 16-angle chunks (128-byte column blocks) written by ONE 3-D TMA op
 constexpr int kTmaGroupBytes = kTmaCB * kTmaTileBytes;
+#ifndef HPEM_ONE_BUFFER_MAX_ANGLES
+#define HPEM_ONE_BUFFER_MAX_ANGLES 128
+#endif
+constexpr int kOneBufferMaxAngles = HPEM_ONE_BUFFER_MAX_ANGLES;   // K1u: single staging buffer per warp up to this angle count
+constexpr int kOneBufferMaxAnglesQuad = 192;                      // ... in the quad-row store mode
+constexpr int kQuadMinAngles = 64;                                // quad-row store mode from this angle count on
 
 struct BeamState {  // per-thread recurrence state of one Gaussian beam
     double ec, rc, gc;     // chunk-start profile value, chunk-start ratio, chunk-to-chunk factor
@@ -135,6 +149,26 @@ __device__ __forceinline__ void beam_init(BeamState& b, double h, double a, doub
     b.rc = exp(-b.x);
     b.gc = exp(-double(kChunk * kChunk) * b.x);
     b.ec = 1.0;
+}
+// same for a sweep whose chunks start at angle index o + 16 c, o in {0, 1, 2, 3} per lane (quad-row store mode: the rows of
+// a warp start their 32-byte-aligned body at different angles).  One code path for every offset -- no divergence -- and
+// still five exps: the offset-dependent start values are small powers of u = exp(-x) and of qk = exp(-32 x)
+// (<= 6 extra roundings, a constant ~5e-16 relative factor on the row).  `u` is returned for the lead elements.
+__device__ __forceinline__ double beam_init_offset(BeamState& b, double h, double a, double amp, int o) {
+    const double t = h / a;
+    b.x = t * t;
+    b.amp = amp;
+    const double u = exp(-b.x);
+    b.q = exp(-2.0 * b.x);
+    b.qk = exp(-(2.0 * kChunk) * b.x);
+    b.hh = exp(-(2.0 * kChunk * kChunk) * b.x);
+    const double g0 = exp(-double(kChunk * kChunk) * b.x);
+    const double u2 = u * u, u4 = u2 * u2;
+    // E(o) = u^(o^2), E(o+1)/E(o) = u^(2o+1), E(o+16)/E(o) = g0 * qk^o
+    b.ec = (o == 0) ? 1.0 : (o == 1) ? u : (o == 2) ? u4 : u4 * u4 * u;
+    b.rc = (o == 0) ? u : (o == 1) ? u2 * u : (o == 2) ? u4 * u : u4 * u2 * u;
+    b.gc = (o == 0) ? g0 : (o == 1) ? g0 * b.qk : (o == 2) ? g0 * (b.qk * b.qk) : g0 * (b.qk * b.qk * b.qk);
+    return u;
 }
 __device__ __forceinline__ void beam_restart(BeamState& b, int i0) {  // exact values at angle index i0
     const double di = double(i0);
@@ -155,35 +189,58 @@ __device__ __forceinline__ void beam_next_chunk(BeamState& b) {
 constexpr int kStoreStg = 0;    // 32x16 tile, transposed read-back, plain streaming stores (any A, any alignment)
 constexpr int kStoreTma = 1;    // 128B-swizzled sub-tiles, TMA tensor stores (even A, 16-byte aligned base)
 constexpr int kStoreRows = 2;   // whole rows of the warp's 32 samples (dense 32 x A tile), ONE contiguous 1-D bulk store
-                                // per warp: the mode for small odd A (the reference's 91), where no tensor map exists
+                                // per warp (small odd A when the pair-row mode is switched off)
+constexpr int kStoreQuad = 3;   // row pitch not a multiple of 32 bytes (A % 4 != 0, the reference's 91 included).
+// Partial 32-byte sectors are what a store stream must avoid on B200: (n, A) tensor boxes over rows that start mid-sector
+// run at 4.4 TB/s where sector-aligned rows reach 5.6 (A = 198/202 vs 200), and odd A has no (n, A) tensor map at all
+// (rows only 8-byte aligned).  But FOUR consecutive rows always span a multiple of 32 bytes.  So the rows of a warp are
+// split by phase (sample index mod 4): phase f skips lead[f] elements to reach a sector boundary, owns a "body" of
+// q_body (multiple of 4) elements that IS sector-aligned, and leaves tail[f] elements.  Each phase gets its own tensor
+// maps over the quad-row view (n/4 rows of pitch 4A, base = first body element of the phase), lanes are permuted so that
+// quarter-warp f holds 8 rows of phase f (one 128B-swizzle atom per column block), and the chunked sweep of a lane simply
+// starts at angle lead[f].  The tail of row r and the lead of row r+1 are contiguous in memory and together fill whole
+// sectors: they go through a small per-warp shared-memory buffer and are written by 4-8 adjacent lanes per boundary.
+constexpr int kBsecSlots = 8;                       // <= 7 tail + 3 lead elements, always 0, 4 or 8 per row boundary
+constexpr int kBsecBytes = 32 * kBsecSlots * 8;     // per warp
 
-template <bool WANT_PLUME, bool STORE_J, int MODE>
-__global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_kernel(const EvalParams p,
-                                                                 const __grid_constant__ CUtensorMap jmap,
-                                                                 const __grid_constant__ CUtensorMap jmap3) {
+// NBUF staging buffers per warp: 2 overlap the fill of one group with the TMA read of the other (best for long rows);
+// 1 halves shared memory and almost doubles the resident warps, which wins while the per-sample prologue dominates
+// (A <~ 128: 0.120 ms vs 0.148 ms at 1e6 x 64, B200)
+template <bool WANT_PLUME, bool STORE_J, int MODE, int NBUF>
+__global__ void __launch_bounds__(kThreadsU, NBUF == 1 ? 10 : HPEM_MIN_BLOCKS_U)
+eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // layout: [staging tiles (1024-byte aligned for the 128B TMA swizzle)] [fused weights]
+    // layout: [staging tiles (1024-byte aligned for the 128B TMA swizzle)] [row-boundary buffers (quad mode)] [fused weights]
     unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    constexpr bool USE_TMA = (MODE == kStoreTma);
+    constexpr bool QUAD = (MODE == kStoreQuad);
+    constexpr bool USE_TMA = (MODE == kStoreTma) || QUAD;
     constexpr bool ROWS = (MODE == kStoreRows);
-    const int stage_bytes_per_warp = USE_TMA ? kTmaBuffers * kTmaGroupBytes
+    constexpr int kGroupBytes = kTmaGroupBytes;
+    const int stage_bytes_per_warp = USE_TMA ? NBUF * kGroupBytes
                                              : (ROWS ? ((32 * p.n_angles * 8 + 15) & ~15) : 32 * kTilePitch * 8);
     const int stage_bytes = STORE_J ? kWarpsU * stage_bytes_per_warp : 0;
-    double2* wsm = reinterpret_cast<double2*>(smem_al + stage_bytes);
+    const int bsec_bytes = (STORE_J && QUAD) ? kWarpsU * kBsecBytes : 0;
+    double2* wsm = reinterpret_cast<double2*>(smem_al + stage_bytes + bsec_bytes);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     unsigned char* stage = smem_al + warp * stage_bytes_per_warp;
+    double* bsec = reinterpret_cast<double*>(smem_al + stage_bytes + warp * kBsecBytes);   // [32 boundaries][8 slots]
 
     if (WANT_PLUME) {
         for (int i = threadIdx.x; i < p.n_angles_pad; i += kThreadsU) wsm[i] = p.w[i];
         __syncthreads();
     }
 
-    const long long s_raw = (long long)blockIdx.x * kThreadsU + threadIdx.x;
+    // which of the warp's 32 samples this lane owns.  Quad mode: quarter-warp f (lanes 8f .. 8f+7) takes the samples of
+    // phase f, lane 8f+q the one in quad-row q -- conflict-free 16-byte stores into one swizzle atom per phase
+    const int phase = QUAD ? lane >> 3 : 0;
+    const int prl = QUAD ? lane & 7 : lane;      // row of this lane inside its staging sub-tile
+    const int lidx = QUAD ? 4 * prl + phase : lane;
+    const long long warp_s0 = (long long)blockIdx.x * kThreadsU + warp * 32;
+    const long long s_raw = warp_s0 + lidx;
     const bool active = s_raw < p.n;
     const long long s = active ? s_raw : p.n - 1;  // inactive lanes shadow the last sample, never store
-    const long long warp_s0 = s_raw - lane;
     if (warp_s0 >= p.n) return;  // whole warp out of range (after the only __syncthreads)
 
     // all per-sample loads are issued up front (15 independent LDG.64 in flight per thread)
@@ -206,9 +263,16 @@ __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_ker
     double j_cex, base;
     cex_terms(k.density, x_in[IN_sigma], x_in[IN_I_B0], p.radius0, j_cex, base);
 
+    const int off = QUAD ? p.q_lead[phase] : 0;  // angle index of the chunked sweep's first element
     BeamState b1, b2;
-    beam_init(b1, p.h, k.a1, __dmul_rn(base, k.amp1));   // (base_density * A1), plume.py:99
-    beam_init(b2, p.h, k.a2, __dmul_rn(base, k.amp2));   // (base_density * A2), plume.py:100
+    double u1 = 0.0, u2 = 0.0;                   // exp(-x) of the two beams (quad mode: the lead elements need E(1), E(2))
+    if (QUAD) {
+        u1 = beam_init_offset(b1, p.h, k.a1, __dmul_rn(base, k.amp1), off);
+        u2 = beam_init_offset(b2, p.h, k.a2, __dmul_rn(base, k.amp2), off);
+    } else {
+        beam_init(b1, p.h, k.a1, __dmul_rn(base, k.amp1));   // (base_density * A1), plume.py:99
+        beam_init(b2, p.h, k.a2, __dmul_rn(base, k.amp2));   // (base_density * A2), plume.py:100
+    }
 
     const bool known_invalid = (k.a1 <= 0.0);  // plume.py:105 first term
     // With non-negative beam amplitudes and a positive CEX floor every j_ion is > 0 (or NaN), so the per-angle
@@ -218,27 +282,54 @@ __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_ker
     double num = 0.0, den = 0.0;
 
     const int A = p.n_angles;
-    const int n_chunks = (A + kChunk - 1) / kChunk;
+    const int A_sweep = QUAD ? p.q_body : A;     // angles covered by the chunked sweep
+    const int n_chunks = (A_sweep + kChunk - 1) / kChunk;
     const int rows_valid = (int)min((long long)32, p.n - warp_s0);
     const int col = lane & (kChunk - 1);
     const int rsub = lane >> 4;
+    const int tma_row0 = QUAD ? (int)(warp_s0 >> 2) : (int)warp_s0;
+    double tail_e1 = 0.0, tail_e2 = 0.0, tail_r1 = 0.0, tail_r2 = 0.0;   // recurrence state one step past the sweep (quad mode)
+
+    // one element outside the chunked sweep (quad mode): quadrature, validity test, value into the row-boundary buffer
+    auto edge_element = [&](double sum, int angle, int slot_row, int slot) {
+        const double j = sum + j_cex;
+        const double2 w = wsm[angle];
+        den = fma(w.x, sum, den);
+        num = fma(w.y, sum, num);
+        bad |= (j <= 0.0);
+        if (STORE_J) bsec[slot_row * kBsecSlots + slot] = known_invalid ? kInvalidFill : j;
+    };
+    if (QUAD && off > 0) {
+        // lead elements (angles 0 .. off-1 <= 2): E(0) = 1, E(1) = u, E(2) = u^4.  They complete the sector(s) that the
+        // previous row's tail starts: boundary lidx-1, after that row's tail[phase-1] slots.
+        const int t_prev = p.q_tail[(phase + 3) & 3];
+        edge_element(b1.amp + b2.amp, 0, lidx - 1, t_prev);
+        if (off > 1) edge_element(b1.amp * u1 + b2.amp * u2, 1, lidx - 1, t_prev + 1);
+        if (off > 2) {
+            const double v1 = u1 * u1, v2 = u2 * u2;
+            edge_element(b1.amp * (v1 * v1) + b2.amp * (v2 * v2), 2, lidx - 1, t_prev + 2);
+        }
+    }
 
     auto chunk_loop = [&](auto checked_tag) {
         constexpr bool CHECKED = decltype(checked_tag)::value;
         for (int c = 0; c < n_chunks; ++c) {
             const int i0 = c * kChunk;
             if (c != 0 && (c % kRestartChunks) == 0) {  // exact restart bounds the recurrence error for large A
-                beam_restart(b1, i0);
-                beam_restart(b2, i0);
+                beam_restart(b1, i0 + off);
+                beam_restart(b2, i0 + off);
             }
             double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec;
             double r1 = b1.rc, r2 = b2.rc;
-            const int kcount = min(kChunk, A - i0);
-            // TMA staging: [buffer][column block within the group][32 rows][128 B, 16-byte chunks XOR-swizzled by row]
-            unsigned char* group_buf = stage + ((c / kTmaCB) % kTmaBuffers) * kTmaGroupBytes;
+            const int kcount = min(kChunk, A_sweep - i0);
+            // TMA staging: [buffer][phase (quad mode)][column block within the group][rows][128 B, 16-byte chunks XOR-swizzled by row]
+            unsigned char* group_buf = stage + ((c / kTmaCB) % NBUF) * kGroupBytes;
             // kStoreRows: dense [32][A] tile; for odd A the row pitch A*8 bytes walks all 16 bank pairs -> conflict-free
-            unsigned char* my_row = USE_TMA ? group_buf + (c % kTmaCB) * kTmaTileBytes + lane * (kChunk * 8)
-                                            : (ROWS ? stage + (size_t(lane) * A + i0) * 8 : stage + lane * (kTilePitch * 8));
+            unsigned char* my_row =
+                QUAD ? group_buf + phase * (kTmaCB * 1024) + (c % kTmaCB) * 1024 + prl * (kChunk * 8)
+                     : (USE_TMA ? group_buf + (c % kTmaCB) * kTmaTileBytes + lane * (kChunk * 8)
+                                : (ROWS ? stage + (size_t(lane) * A + i0) * 8 : stage + lane * (kTilePitch * 8)));
+            const double2* wrow = wsm + i0 + off;
             auto step = [&](double2 w, double& jout) {
                 const double sum = e1 + e2;    // j_beam + j_scat
                 const double j = sum + j_cex;  // plume.py:102
@@ -257,11 +348,11 @@ __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_ker
 #pragma unroll
                 for (int kk = 0; kk < kChunk; kk += 2) {
                     double ja, jb;
-                    step(wsm[i0 + kk], ja);
-                    step(wsm[i0 + kk + 1], jb);
+                    step(wrow[kk], ja);
+                    step(wrow[kk + 1], jb);
                     if (STORE_J) {
                         if (USE_TMA) {
-                            *reinterpret_cast<double2*>(my_row + ((((kk >> 1) ^ (lane & 7))) << 4)) = make_double2(ja, jb);
+                            *reinterpret_cast<double2*>(my_row + ((((kk >> 1) ^ (prl & 7))) << 4)) = make_double2(ja, jb);
                         } else {
                             reinterpret_cast<double*>(my_row)[kk] = ja;
                             reinterpret_cast<double*>(my_row)[kk + 1] = jb;
@@ -271,39 +362,54 @@ __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_ker
             } else {
                 for (int kk = 0; kk < kcount; ++kk) {
                     double ja;
-                    step(wsm[i0 + kk], ja);
+                    step(wrow[kk], ja);
                     if (STORE_J) {
                         if (USE_TMA)
-                            *reinterpret_cast<double*>(my_row + ((((kk >> 1) ^ (lane & 7))) << 4) + ((kk & 1) << 3)) = ja;
+                            *reinterpret_cast<double*>(my_row + ((((kk >> 1) ^ (prl & 7))) << 4) + ((kk & 1) << 3)) = ja;
                         else
                             reinterpret_cast<double*>(my_row)[kk] = ja;
                     }
                 }
+            }
+            if (QUAD) {
+                tail_e1 = e1; tail_e2 = e2;
+                tail_r1 = r1; tail_r2 = r2;
             }
             beam_next_chunk(b1);
             beam_next_chunk(b2);
 
             if (STORE_J) {
                 if (USE_TMA) {
-                    // kTmaCB chunks are shipped by ONE 3-D TMA op: 32 rows x (kTmaCB x 128 B) contiguous row pieces
+                    // kTmaCB chunks are shipped by ONE 3-D TMA op (per phase): rows x (kTmaCB x 128 B) contiguous row pieces
                     // (6.2-6.5 TB/s on B200 against 5.6 TB/s for single 128-byte pieces, tools/store_pattern.cu).
                     // A trailing group that is incomplete or holds the partial last column block goes out as 2-D
-                    // 32x16 boxes, whose tensor map clips columns >= A.  Rows >= n are clipped by both maps.
+                    // boxes of 16 columns, whose tensor map clips columns >= A_sweep.  Rows >= n are clipped by all maps.
                     const bool last_chunk = (c == n_chunks - 1);
                     if ((c % kTmaCB) == kTmaCB - 1 || last_chunk) {
                         fence_async_smem();
                         __syncwarp();
                         if (lane == 0) {
                             const int c_first = c - (c % kTmaCB);
-                            if (c_first + kTmaCB <= A / kChunk) {
-                                tma_issue_3d(&jmap3, smem_u32(group_buf), 0, (int)warp_s0, c_first);
+                            const bool whole = c_first + kTmaCB <= A_sweep / kChunk;
+                            if (QUAD) {
+#pragma unroll
+                                for (int f = 0; f < 4; ++f) {
+                                    const uint32_t src = smem_u32(group_buf + f * (kTmaCB * 1024));
+                                    if (whole) {
+                                        tma_issue_3d(&maps.m3[f], src, 0, tma_row0, c_first);
+                                    } else {
+                                        for (int cc = c_first; cc <= c; ++cc)
+                                            tma_issue_2d(&maps.m2[f], src + (cc - c_first) * 1024, cc * kChunk, tma_row0);
+                                    }
+                                }
+                            } else if (whole) {
+                                tma_issue_3d(&maps.m3[0], smem_u32(group_buf), 0, tma_row0, c_first);
                             } else {
                                 for (int cc = c_first; cc <= c; ++cc)
-                                    tma_issue_2d(&jmap, smem_u32(group_buf + (cc - c_first) * kTmaTileBytes), cc * kChunk,
-                                                 (int)warp_s0);
+                                    tma_issue_2d(&maps.m2[0], smem_u32(group_buf + (cc - c_first) * kTmaTileBytes), cc * kChunk, tma_row0);
                             }
                             tma_commit();
-                            tma_wait_read<kTmaBuffers - 1>();   // the other group buffer is free again
+                            tma_wait_read<NBUF - 1>();   // the buffer the next group goes into is free again
                         }
                         __syncwarp();
                     }
@@ -326,6 +432,33 @@ __global__ void __launch_bounds__(kThreadsU, HPEM_MIN_BLOCKS_U) eval_uniform_ker
         chunk_loop(std::true_type{});
     else
         chunk_loop(std::false_type{});
+
+    if (QUAD) {
+        // tail elements (angles off + q_body .. A-1, at most 7): the recurrence simply continues.  They open the
+        // sector(s) that the next row's lead completes: boundary lidx, slots 0 .. tail-1.
+        const int n_tail = p.q_tail[phase];
+        const int a0 = off + A_sweep;
+        for (int t = 0; t < n_tail; ++t) {
+            edge_element(tail_e1 + tail_e2, a0 + t, lidx, t);
+            tail_e1 *= tail_r1; tail_r1 *= b1.q;
+            tail_e2 *= tail_r2; tail_r2 *= b2.q;
+        }
+        if (STORE_J) {
+            // write the row boundaries: boundary r = tail of row r + lead of row r+1, contiguous in memory and a whole
+            // number of sectors; 8 lanes per boundary, so each sector is written by adjacent lanes of one instruction
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < kBsecSlots; ++it) {
+                const int e = it * 32 + lane;
+                const int r = e >> 3, slot = e & 7;
+                const int f = r & 3;
+                const int t_r = p.q_tail[f];
+                const int cnt = t_r + p.q_lead[(f + 1) & 3];
+                if (slot < cnt && warp_s0 + r < p.n)   // n % 4 == 0: row r+1 exists whenever its lead is non-empty
+                    __stcs(p.j_ion + (warp_s0 + r + 1) * (long long)A - t_r + slot, bsec[r * kBsecSlots + slot]);
+            }
+        }
+    }
 
     if (STORE_J && ROWS) {   // ship the warp's rows: rows_valid * A * 8 contiguous bytes starting at a 16-byte aligned address
         const uint32_t bytes = (uint32_t)rows_valid * (uint32_t)A * 8u;

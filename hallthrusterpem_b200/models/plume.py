@@ -9,7 +9,7 @@ __all__ = ['current_density', 'plume_cathode']
 
 def current_density(inputs: dict, sweep_radius=1.0, *, n_angles: int = 91, torr_2_pa: float | None = None,
                     device: int | None = None, direct: bool = False, extras: bool = False, no_tma: bool = False,
-                    lanes1: bool = False, lanes4: bool = False) -> dict:
+                    lanes1: bool = False, lanes4: bool = False, no_quad: bool = False) -> dict:
     """Semi-empirical ion current density (j_ion) plume model over a 90 deg sweep (0 deg = thruster centerline),
     plus the plume divergence angle and, if `T` is given, the divergence-corrected thrust.
 
@@ -23,21 +23,22 @@ def current_density(inputs: dict, sweep_radius=1.0, *, n_angles: int = 91, torr_
     :param lanes1: force the one-lane-per-sample sweep kernel (K1u); `lanes4` forces the four-lane one (K1v).
                    By default the library picks per angle count (diagnostics).
     :param no_tma: stage `j_ion` with plain global stores instead of TMA tensor stores (diagnostics).
+    :param no_quad: angle counts that are not a multiple of 4: skip the quad-row tensor stores (diagnostics).
     :param extras: also return `cos_div` and the whole-sample `invalid` mask (plume.py:105,124).
     :returns outputs: `j_ion` (..., A[, R]), `div_angle` (...[, R]), optionally `T_c`, and `j_ion_coords`
                       (object array of loop shape whose elements are the angle grid in radians).
     """
     return evaluate(inputs, want_cathode=False, want_plume=True, sweep_radius=sweep_radius, n_angles=n_angles,
                     torr=torr_2_pa, device=device, direct=direct, extras=extras, no_tma=no_tma,
-                    lanes1=lanes1, lanes4=lanes4)
+                    lanes1=lanes1, lanes4=lanes4, no_quad=no_quad)
 
 
 def plume_cathode(inputs: dict, sweep_radius=1.0, *, n_angles: int = 91, torr_2_pa: float | None = None,
                   device: int | None = None, direct: bool = False, extras: bool = False,
                   want_j_ion: bool = True, no_tma: bool = False, lanes1: bool = False,
-                  lanes4: bool = False) -> dict:
+                  lanes4: bool = False, no_quad: bool = False) -> dict:
     """The PEM v0 chain Cathode -> (Thruster, external) -> Plume in ONE fused launch over the same samples
     (pem_v0_SPT-100.yml:5,62,215): returns `V_cc` together with the plume outputs.  `P_b` is loaded once."""
     return evaluate(inputs, want_cathode=True, want_plume=True, sweep_radius=sweep_radius, n_angles=n_angles,
                     torr=torr_2_pa, device=device, direct=direct, extras=extras, want_j_ion=want_j_ion,
-                    no_tma=no_tma, lanes1=lanes1, lanes4=lanes4)
+                    no_tma=no_tma, lanes1=lanes1, lanes4=lanes4, no_quad=no_quad)

@@ -93,6 +93,9 @@ typedef struct hpem_outputs {
 #define HPEM_FLAG_LANES4 8u       /* force the recurrence kernel with FOUR lanes per sample in the sweep (K1v,      \
                                      whole rows per bulk store); default for odd angle counts */
 
+#define HPEM_FLAG_NO_QUAD 16u      /* angle counts that are not a multiple of 4: do not use K1u's quad-row tensor     \
+                                     stores (diagnostics; falls back to (n, A) boxes / whole-row bulk stores) */
+
 typedef struct hpem_grid hpem_grid; /* opaque */
 
 int hpem_abi_version(void);

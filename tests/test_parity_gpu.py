@@ -13,8 +13,9 @@ from tests import parity
 pytestmark = pytest.mark.gpu
 
 GOLDEN = sorted((Path(__file__).parent / 'golden').glob('*.npz'))
-# kernel variants: K1v (default, TMA / plain stores), K1u (one lane per sample), K1d (reference operation order)
-MODES = {'default': {}, 'lanes4': {'lanes4': True}, 'lanes4_stg': {'lanes4': True, 'no_tma': True},
+# kernel variants: default (K1u with (n, A) / quad-row tensor stores, whole-row mode for small odd A), K1v (four lanes per
+# sample), K1u with plain stores, the pre-quad fallbacks, K1d (reference operation order)
+MODES = {'default': {}, 'no_quad': {'no_quad': True}, 'lanes4': {'lanes4': True}, 'lanes4_stg': {'lanes4': True, 'no_tma': True},
          'lanes1': {'lanes1': True}, 'lanes1_stg': {'lanes1': True, 'no_tma': True}, 'direct': {'direct': True}}
 
 
@@ -288,3 +289,57 @@ def test_nonuniform_grid_uses_direct_kernel(cuda_device):
     g2 = GridHandle(0, 91, np.array([1.0]), alpha=alpha)
     assert not g2.uniform
     g2.close()
+
+
+@pytest.mark.parametrize('n_angles', [64 + 2, 91, 93, 99, 130, 255, 511])
+@pytest.mark.parametrize('n', [4, 5, 7, 63, 1001, 4099])
+def test_quad_row_store_mode(n, n_angles, cuda_device):
+    """Angle counts that are not a multiple of 4 (rows start mid-sector; the reference's 91 among them) go through K1u's
+    quad-row tensor stores: every row phase, ragged sample counts (n % 4 != 0 peels 1-3 samples off), edge rows mixed in."""
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    from oracle.make_golden import edge_batch
+    from oracle.ref_restated import cathode_coupling_oracle, current_density_oracle
+    _, _, plume_cathode = _models()
+    torr = 133.322
+    b = spt100_batch(n, 31 * n + n_angles)
+    if n >= 1001:                      # invalid / NaN / late-invalid rows land in different phases and warps
+        e = edge_batch()
+        k = len(e['P_b'])
+        b = {key: np.concatenate([b[key][:300], e[key], b[key][300:n - k]]) for key in b}
+    with np.errstate(all='ignore'):
+        ref = current_density_oracle(b, 1.0, n_angles, torr, with_coords=False, return_internals=True)
+        ref['V_cc'] = cathode_coupling_oracle(b, torr)['V_cc']
+    g = {'j_ion': ref['j_ion'], 'div_angle': ref['div_angle'], 'T_c': ref['T_c'], 'cos_div': ref['_cos_div'],
+         'invalid': ref['_invalid'], 'V_cc': ref['V_cc']}
+    out = plume_cathode(b, 1.0, n_angles=n_angles, torr_2_pa=torr, extras=True)
+    _compare(out, g, b, torr, np.array([1.0]), f'quad n{n} a{n_angles}')
+
+
+def test_quad_row_mode_device_offsets_and_full_size(cuda_device):
+    """Device path: an output buffer that is only 8-byte aligned must fall back (no tensor stores) with identical values;
+    at 1e6 x 91 (the reference's angle count) the quad-row kernel agrees with the reference-order direct kernel."""
+    import ctypes
+    import torch
+    from hallthrusterpem_b200 import _lib
+    from hallthrusterpem_b200.engine import PreparedCall
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    _, current_density, _ = _models()
+    n, A = 1_000_000, 91
+    b = {k: torch.as_tensor(v, device='cuda:0') for k, v in spt100_batch(n, 91).items()}
+    fast = current_density(b, 1.0, n_angles=A, extras=True)
+    direct = current_density(b, 1.0, n_angles=A, extras=True, direct=True)
+    rel = ((fast['j_ion'] - direct['j_ion']).abs() / direct['j_ion'].abs()).max().item()
+    assert rel < 2e-13, rel
+    assert torch.equal(fast['invalid'], direct['invalid'])
+    assert ((fast['cos_div'] - direct['cos_div']).abs() / direct['cos_div'].abs()).max().item() < 1e-13
+    # misaligned output: same call writing into a view that starts 8 bytes into an allocation
+    m = 4096
+    small = {k: v[:m] for k, v in b.items()}
+    call = PreparedCall(small, want_cathode=False, want_plume=True, sweep_radius=1.0, n_angles=A)
+    backing = torch.zeros(m * A + 1, dtype=torch.float64, device='cuda:0')
+    call.out.j_ion = backing[1:].data_ptr()
+    assert call.out.j_ion % 16 == 8
+    call.run()
+    torch.cuda.synchronize()
+    assert torch.equal(backing[1:].view(m, A), fast['j_ion'][:m]) or \
+        ((backing[1:].view(m, A) - fast['j_ion'][:m]).abs() / fast['j_ion'][:m].abs()).max().item() < 2e-13

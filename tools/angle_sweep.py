@@ -14,7 +14,7 @@ n = 1_000_000
 b = {k: torch.as_tensor(v, device='cuda:0') for k, v in spt100_batch(n, 1).items()}
 for A in [int(a) for a in sys.argv[1:]] or [64, 96, 128, 176, 184, 192, 200, 208, 216, 224, 256, 320, 384, 512]:
     row = []
-    for kw in ({}, {'want_j_ion': False}, {'lanes4': True}):
+    for kw in ({}, {'want_j_ion': False}, {'lanes4': True}, {'no_quad': True}):
         call = PreparedCall(b, want_cathode=True, want_plume=True, sweep_radius=1.0, n_angles=A, **kw)
         for _ in range(3):
             call.run()
@@ -26,4 +26,4 @@ for A in [int(a) for a in sys.argv[1:]] or [64, 96, 128, 176, 184, 192, 200, 208
         row.append(float(np.median(ts)))
         del call
     gb = (8 + 144 / A) * n * A / 1e9
-    print(f'A={A:4d}  default {row[0]:.3f} ms ({gb / row[0]:.2f} TB/s)  no-store {row[1]:.3f} ms  lanes4 {row[2]:.3f} ms ({gb / row[2]:.2f} TB/s)', flush=True)
+    print(f'A={A:4d}  default {row[0]:.3f} ms ({gb / row[0]:.2f} TB/s)  no-store {row[1]:.3f} ms  lanes4 {row[2]:.3f} ms ({gb / row[2]:.2f} TB/s)  no-quad {row[3]:.3f} ms', flush=True)

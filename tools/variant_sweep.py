@@ -22,7 +22,7 @@ def run(n, A, want_j=True, reps=12):
         e0.record(); call.run(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return float(np.median(ts))
 print('%%-12s' %% sys.argv[1], ' '.join('%%s=%%.3f' %% (lbl, run(*cfg)) for lbl, cfg in [
-    ('1Mx200', (1000000, 200)), ('1Mx200ns', (1000000, 200, False)), ('1Mx91', (1000000, 91)), ('4Mx256', (4000000, 256))]), flush=True)
+    ('1Mx200', (1000000, 200)), ('1Mx96', (1000000, 96)), ('1Mx64', (1000000, 64)), ('4Mx256', (4000000, 256)), ('1Mx512', (1000000, 512))]), flush=True)
 ''' % str(ROOT)
 for lib in sorted((ROOT / 'build' / 'variants').glob('libhpem_*.so')):
     env = dict(os.environ, HPEM_LIBRARY=str(lib))
