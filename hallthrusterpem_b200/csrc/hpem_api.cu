@@ -219,7 +219,21 @@ int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store
     const bool use_uniform = g.uniform && g.n_radii == 1 && g.smem_ok && !(flags & HPEM_FLAG_FORCE_DIRECT);
     const bool use_multi = plume && store_j && g.uniform && g.n_radii > 1 && g.n_radii <= kMaxRadiiFast && g.smem_ok &&
                            !(flags & HPEM_FLAG_FORCE_DIRECT);
-    if (use_multi) {   // K1r: several radii through the recurrence sweep
+    const size_t smem_w = k1w_smem_bytes(g.n_angles, g.n_angles_pad, g.n_radii);
+    const bool use_stream = plume && g.n_radii >= kMinRadiiStream && smem_w <= 100 * 1024 && (long long)g.n_angles * g.n_radii < (1LL << 25) &&
+                            !(flags & (HPEM_FLAG_FORCE_DIRECT | HPEM_FLAG_LANES1));
+    if (use_stream) {   // K1w: many radii -- per-sample tables + one contiguous store stream per 8 samples (any grid)
+        const unsigned blocks = (unsigned)((p.n + kThreadsW - 1) / kThreadsW);
+        if (g.uniform) {
+            int rc = set_smem(eval_radii_stream_kernel<true>, smem_w);
+            if (rc != HPEM_OK) return rc;
+            eval_radii_stream_kernel<true><<<blocks, kThreadsW, smem_w, st>>>(p);
+        } else {
+            int rc = set_smem(eval_radii_stream_kernel<false>, smem_w);
+            if (rc != HPEM_OK) return rc;
+            eval_radii_stream_kernel<false><<<blocks, kThreadsW, smem_w, st>>>(p);
+        }
+    } else if (use_multi) {   // K1r: a few radii through the recurrence sweep
         const unsigned blocks = (unsigned)((p.n + kThreadsU - 1) / kThreadsU);
         const long long row_len = (long long)g.n_angles * g.n_radii;
         const size_t rad_bytes = size_t(2) * g.n_radii * kThreadsU * sizeof(double);

@@ -963,6 +963,219 @@ __global__ void __launch_bounds__(kThreadsV, HPEM_MIN_BLOCKS_V) eval_lanes4_kern
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1w: several sweep radii, many of them (R >= 8) -- per-sample tables, then ONE contiguous store stream per 8 samples
+// ---------------------------------------------------------------------------------------------
+// j_ion[s, i, rho] = base(s, rho) * g(s, i) + j_cex(s, rho) with g = A1 E1 + A2 E2 (plume.py:95-102): R outputs cost one
+// profile value, so with many radii the kernel is nothing but a store stream -- and a store stream on B200 wants whole
+// 32-byte sectors (see kStoreQuad).  The rows of 8 consecutive samples are contiguous in memory and start sector-aligned,
+// so a warp builds the two small tables of its 8 samples in shared memory -- g (8 x A; the stride-4 recurrence of K1v on the uniform grid, the reference's own
+// divide / square / negate / exp on any other grid) and (base, j_cex) (8 x R) -- and then writes the 8 rows as ONE flat stream: lane l stores
+// elements l, l+32, ... (256 contiguous bytes per instruction), whatever the parity of A*R.  Per warp:
+//   phase 1  lane t <-> sample s0+t : loads, cathode, A1/A2, divergence angles
+//   phase 2  4 groups of 8 samples  : 2a  lane (r, q) = (sample, angle mod 4): g table + the two Simpson sums
+//                                     2b  lanes over (sample, radius): CEX terms, cos_div / div_angle / T_c
+//                                     2c  lanes over the flat (sample, angle, radius) stream: j_ion
+constexpr int kThreadsW = 64;
+constexpr int kWarpsW = kThreadsW / 32;
+constexpr int kGroupW = 8;
+constexpr int kXw = 27;                 // doubles per sample handed from phase 1: amp1 amp2 a1 a2 density sigma I_B0 T flags,
+                                        // and (uniform grids) 8 base exps per beam + x1 x2 for the four-lane recurrence of K1v
+constexpr int kMinRadiiStream = 8;
+
+__host__ __device__ inline size_t k1w_warp_bytes(int n_angles, int n_radii) {
+    return size_t(32) * kXw * 8 + size_t(kGroupW) * n_angles * 8 + size_t(kGroupW) * n_radii * 16 + size_t(kGroupW) * 16;
+}
+__host__ __device__ inline size_t k1w_smem_bytes(int n_angles, int n_angles_pad, int n_radii) {
+    return size_t(n_angles_pad) * 16 + size_t(n_angles) * 8 + size_t(n_radii) * 8 + kWarpsW * k1w_warp_bytes(n_angles, n_radii) + 64;
+}
+
+template <bool UNIFORM>
+__global__ void __launch_bounds__(kThreadsW) eval_radii_stream_kernel(const EvalParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int A = p.n_angles, R = p.n_radii;
+    const long long L = (long long)A * R;
+    double2* wsm = reinterpret_cast<double2*>(smem_raw);                 // [n_angles_pad] fused weights
+    double* alpha_sm = reinterpret_cast<double*>(wsm + p.n_angles_pad);  // [A]
+    double* radii_sm = alpha_sm + A;                                     // [R]
+    unsigned char* wbase = reinterpret_cast<unsigned char*>(radii_sm + R);
+    wbase += (16 - (smem_u32(wbase) & 15)) & 15;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* mine = wbase + warp * k1w_warp_bytes(A, R);
+    double* xch = reinterpret_cast<double*>(mine);                       // [32][kXw]
+    double* gt = xch + 32 * kXw;                                         // [8][A]
+    double2* br = reinterpret_cast<double2*>(gt + kGroupW * A);          // [8][R] (base, j_cex)
+    double2* sums = br + kGroupW * R;                                    // [8] (num, den)
+
+    for (int i = threadIdx.x; i < p.n_angles_pad; i += kThreadsW) wsm[i] = p.w[i];
+    for (int i = threadIdx.x; i < A; i += kThreadsW) alpha_sm[i] = p.alpha[i];
+    for (int i = threadIdx.x; i < R; i += kThreadsW) radii_sm[i] = p.radii[i];
+    __syncthreads();
+
+    const long long warp_s0 = (long long)blockIdx.x * kThreadsW + warp * 32;
+    if (warp_s0 >= p.n) return;
+    // ---------------- phase 1: one lane per sample ----------------
+    {
+        const long long s_raw = warp_s0 + lane;
+        const bool active = s_raw < p.n;
+        const long long s = active ? s_raw : p.n - 1;
+        double x_in[kNumInputs];
+#pragma unroll
+        for (int q = 0; q < kNumInputs; ++q) {
+            const bool needed = (q == IN_P_b) || (q <= IN_P_T ? p.v_cc != nullptr : (q == IN_T ? p.t_c != nullptr : true));
+            x_in[q] = needed ? load_in(p, q, s) : 0.0;
+        }
+        if (p.v_cc) {
+            const double v = cathode_vcc(x_in[IN_P_b], x_in[IN_V_a], x_in[IN_T_e], x_in[IN_V_vac], x_in[IN_Pstar],
+                                         x_in[IN_P_T], p.torr);
+            if (active) p.v_cc[s] = v;
+        }
+        const SampleConsts k = plume_sample_consts(x_in[IN_P_b], x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3],
+                                                   x_in[IN_c4], x_in[IN_c5], p.torr);
+        double* xr = xch + lane * kXw;
+        xr[0] = k.amp1; xr[1] = k.amp2; xr[2] = k.a1; xr[3] = k.a2; xr[4] = k.density;
+        xr[5] = x_in[IN_sigma]; xr[6] = x_in[IN_I_B0]; xr[7] = x_in[IN_T];
+        xr[8] = (k.a1 <= 0.0) ? 1.0 : 0.0;          // plume.py:105 first term
+        if (UNIFORM) {                               // start values of the stride-4 Gaussian recurrence (see K1v)
+            const double t1 = p.h / k.a1, t2 = p.h / k.a2;
+            const double x1 = t1 * t1, x2 = t2 * t2;
+            double ex[8];
+            beam_base_exps(x1, ex);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xr[9 + j] = ex[j];
+            beam_base_exps(x2, ex);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xr[17 + j] = ex[j];
+            xr[25] = x1;
+            xr[26] = x2;
+        }
+    }
+    __syncwarp();
+
+    // ---------------- phase 2: groups of 8 samples ----------------
+#pragma unroll 1
+    for (int g = 0; g < 32 / kGroupW; ++g) {
+        const long long gs0 = warp_s0 + g * kGroupW;
+        if (gs0 >= p.n) break;   // warp-uniform
+        const int nvalid = (int)min((long long)kGroupW, p.n - gs0);
+        const double* xg = xch + g * kGroupW * kXw;
+        // 2a: g(s, i) = A1 exp(-(alpha_i/a1)^2) + A2 exp(-(alpha_i/a2)^2) in the reference's operation order (plume.py:99-100
+        // without the radius-dependent factor), and the two fused Simpson sums of plume.py:117-123
+        {
+            const int r = lane >> 2, q = lane & 3;
+            const double* xr = xg + r * kXw;
+            const double amp1 = xr[0], amp2 = xr[1], a1 = xr[2], a2 = xr[3];
+            double num = 0.0, den = 0.0;
+            if (UNIFORM) {       // lane q sweeps angles i = q (mod 4) with the stride-4 recurrence of K1v
+                BeamLane b1, b2;
+                b1.amp = amp1; b2.amp = amp2;
+                b1.x = xr[25]; b2.x = xr[26];
+                beam_lane_init(b1, xr + 9, q);
+                beam_lane_init(b2, xr + 17, q);
+                const int n_ch = (A + kCols4 - 1) / kCols4;
+                for (int c = 0; c < n_ch; ++c) {
+                    const int i0 = c * kCols4;
+                    if (c != 0 && (c % kRestartChunks4) == 0) {
+                        beam_lane_restart(b1, i0 + q);
+                        beam_lane_restart(b2, i0 + q);
+                    }
+                    double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec, r1 = b1.rc, r2 = b2.rc;
+#pragma unroll
+                    for (int m = 0; m < kSteps4; ++m) {
+                        const int i = i0 + q + kL4 * m;
+                        const double v = e1 + e2;
+                        const double2 w = wsm[i];            // zero beyond A (padding to a multiple of 64)
+                        den = fma(w.x, v, den);
+                        num = fma(w.y, v, num);
+                        if (i < A) gt[r * A + i] = v;
+                        e1 *= r1; r1 *= b1.q;
+                        e2 *= r2; r2 *= b2.q;
+                    }
+                    beam_lane_next(b1);
+                    beam_lane_next(b2);
+                }
+            } else {
+                for (int i = q; i < A; i += 4) {
+                    const double al = alpha_sm[i];
+                    const double t1 = al / a1, t2 = al / a2;
+                    const double v = __dadd_rn(__dmul_rn(amp1, exp(-(t1 * t1))), __dmul_rn(amp2, exp(-(t2 * t2))));
+                    gt[r * A + i] = v;
+                    const double2 w = wsm[i];
+                    den = fma(w.x, v, den);
+                    num = fma(w.y, v, num);
+                }
+            }
+            num += __shfl_xor_sync(0xffffffffu, num, 1);
+            den += __shfl_xor_sync(0xffffffffu, den, 1);
+            num += __shfl_xor_sync(0xffffffffu, num, 2);
+            den += __shfl_xor_sync(0xffffffffu, den, 2);
+            if (q == 0) sums[r] = make_double2(num, den);
+        }
+        __syncwarp();
+        // 2b: per (sample, radius): decay, j_cex, base (plume.py:95-98); cos_div, div_angle, T_c (plume.py:122-127,137)
+        bool needs_check = false;
+        for (int pr = lane; pr < nvalid * R; pr += 32) {
+            const int smp = pr / R, rho = pr - smp * R;
+            const double* xr = xg + smp * kXw;
+            double j_cex, base;
+            cex_terms(xr[4], xr[5], xr[6], radii_sm[rho], j_cex, base);
+            br[smp * R + rho] = make_double2(base, j_cex);
+            // non-negative amplitudes and base, positive CEX floor => every j_ion > 0 (or NaN): no per-element test needed
+            needs_check |= !(xr[0] >= 0.0 && xr[1] >= 0.0 && base >= 0.0 && j_cex > 0.0) || xr[8] != 0.0;
+            const double2 sm = sums[smp];
+            double cd = __dmul_rn(base, sm.x) / __dmul_rn(base, sm.y);
+            if (cd == CUDART_INF) cd = CUDART_NAN;
+            const long long o = (gs0 + smp) * R + rho;
+            if (p.div_angle) p.div_angle[o] = acos(cd);
+            if (p.cos_div) p.cos_div[o] = cd;
+            if (p.t_c) p.t_c[o] = __dmul_rn(xr[7], cd);
+        }
+        needs_check = __any_sync(0xffffffffu, needs_check);
+        __syncwarp();
+        // 2c: the 8 rows as one flat stream of nvalid * A * R elements.  Element e = (q, rho) with q = e / R the flat
+        // (sample, angle) index -- exactly the index into the g table -- advanced incrementally: e += 32.
+        unsigned badbits = 0, knownbits = 0;
+        for (int smp = 0; smp < nvalid; ++smp) knownbits |= (xg[smp * kXw + 8] != 0.0) ? (1u << smp) : 0u;
+        const int total = nvalid * A * R;              // < 2^29 (checked on the host)
+        const int dq = 32 / R, drho = 32 - dq * R;     // e += 32  <=>  q += dq, rho += drho (+ one carry)
+        if (p.j_ion && !needs_check) {
+            double* dst = p.j_ion + gs0 * L;
+            int q = lane / R, rho = lane - q * R;
+            int smp_end = A, br_base = 0;               // first q of the next sample, offset of the current sample's (base, j_cex) row
+#pragma unroll 4
+            for (int e = lane; e < total; e += 32) {
+                while (q >= smp_end) { smp_end += A; br_base += R; }
+                const double2 bj = br[br_base + rho];
+                __stcs(dst + e, fma(bj.x, gt[q], bj.y));   // base * (A1 E1 + A2 E2) + j_cex, plume.py:99-102
+                q += dq;
+                rho += drho;
+                if (rho >= R) { rho -= R; ++q; }
+            }
+        } else {                                        // rare: rows that may hold a non-positive j_ion, or alpha1 <= 0
+            double* dst = p.j_ion ? p.j_ion + gs0 * L : nullptr;
+            for (int e = lane; e < total; e += 32) {
+                const int q = e / R, rho = e - q * R, smp = q / A;
+                const double2 bj = br[smp * R + rho];
+                const double j = fma(bj.x, gt[q], bj.y);
+                if (j <= 0.0) badbits |= 1u << smp;
+                if (dst) __stcs(dst + e, ((knownbits >> smp) & 1u) ? kInvalidFill : j);
+            }
+        }
+        badbits = __reduce_or_sync(0xffffffffu, badbits);
+        __syncwarp();
+        const unsigned late = badbits & ~knownbits;    // plume.py:106 for rows whose non-positive j_ion was found on the way
+        if (p.j_ion && late) {
+            for (int smp = 0; smp < nvalid; ++smp) {
+                if (!((late >> smp) & 1u)) continue;
+                double* row = p.j_ion + (gs0 + smp) * L;
+                for (long long e = lane; e < L; e += 32) row[e] = kInvalidFill;
+            }
+        }
+        if (p.invalid && lane < nvalid) p.invalid[gs0 + lane] = (((badbits | knownbits) >> lane) & 1u) ? 1 : 0;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1d: warp per sample, any grid, any radii, reference operation order
 // ---------------------------------------------------------------------------------------------
 constexpr int kThreadsD = 128;
