@@ -343,3 +343,29 @@ def test_quad_row_mode_device_offsets_and_full_size(cuda_device):
     torch.cuda.synchronize()
     assert torch.equal(backing[1:].view(m, A), fast['j_ion'][:m]) or \
         ((backing[1:].view(m, A) - fast['j_ion'][:m]).abs() / fast['j_ion'][:m].abs()).max().item() < 2e-13
+
+
+@pytest.mark.parametrize('n,n_angles,n_radii', [(1003, 91, 25), (517, 100, 9), (64, 33, 40), (300, 257, 8)])
+def test_many_radii_stream_kernel(n, n_angles, n_radii, cuda_device):
+    """K1w (R >= 8): edge rows (alpha1 <= 0, NaN rows, rows with a non-positive j_ion at some radius) mixed with random
+    samples, ragged groups of 8, odd and even row lengths, against the oracle; every kernel variant."""
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    from oracle.make_golden import edge_batch
+    from oracle.ref_restated import current_density_oracle
+    _, current_density, _ = _models()
+    torr = 133.322
+    b = spt100_batch(n, 7 * n + n_radii, c3_test_range=True)
+    e = edge_batch()
+    k = min(len(e['P_b']), n // 2)
+    b = {key: np.concatenate([b[key][:5], e[key][:k], b[key][5:n - k]]) for key in b}
+    radii = np.sort(np.random.default_rng(n).uniform(0.5, 1.5, n_radii))
+    with np.errstate(all='ignore'):
+        ref = current_density_oracle(b, radii, n_angles, torr, with_coords=False, return_internals=True)
+    for mode in ('default', 'lanes1', 'direct'):
+        out = current_density(b, radii, n_angles=n_angles, torr_2_pa=torr, extras=True, **MODES[mode])
+        assert out['j_ion'].shape == (n, n_angles, n_radii) and out['div_angle'].shape == (n, n_radii)
+        parity.check_j_ion(out['j_ion'], ref['j_ion'], b['I_B0'], radii, ref['_invalid'], f'{mode}:j_ion')
+        assert np.array_equal(np.asarray(out['invalid']).astype(bool), ref['_invalid']), mode
+        parity.check_rel(out['cos_div'], ref['_cos_div'], f'{mode}:cos_div')
+        parity.check_rel(out['T_c'], ref['T_c'], f'{mode}:T_c')
+        parity.check_div_angle(out['div_angle'], ref['div_angle'], out['cos_div'], ref['_cos_div'], f'{mode}:div_angle')
