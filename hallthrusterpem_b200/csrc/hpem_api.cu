@@ -822,7 +822,7 @@ int hpem_measurements_create(const hpem_grid* g, int m, const double* theta, con
         pts[q].y = y[q];
         pts[q].inv_sigma = 1.0 / sigma[q];
         pts[q].orig = q;
-        pts[q].pad = 0;
+        pts[q].lo = hi - 1;
     }
     std::vector<int> order(m);
     for (int q = 0; q < m; ++q) order[q] = q;
@@ -884,7 +884,8 @@ int hpem_loglike(const hpem_grid* g, const hpem_measurements* meas, int64_t n, c
     lp.meas = meas->d_meas;
     lp.loglike = loglike;
     lp.y_pred = y_pred;
-    const size_t smem = sizeof(MeasPoint) * meas->m + sizeof(int) * g->n_angles;
+    const size_t smem = ((sizeof(MeasPoint) * meas->m + sizeof(int) * g->n_angles + 15) & ~size_t(15)) +
+                        size_t(kThreadsL) * kRowL * sizeof(double);
     int rc = set_smem(loglike_kernel, smem);
     if (rc != HPEM_OK) return rc;
     const unsigned blocks = (unsigned)((n + kThreadsL - 1) / kThreadsL);

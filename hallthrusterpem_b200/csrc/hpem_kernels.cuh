@@ -1614,7 +1614,7 @@ struct MeasPoint {       // one probe location, sorted by |theta|
     double y;            // measured j_ion
     double inv_sigma;    // 1 / standard deviation
     int orig;            // index in the caller's arrays
-    int pad;
+    int lo;              // grid interval [alpha[lo], alpha[lo+1]] that holds |theta|
 };
 struct LoglikeParams {
     int m;                    // number of measurement points
@@ -1624,17 +1624,23 @@ struct LoglikeParams {
     double* y_pred;           // (n, m) in the caller's point order, or nullptr
 };
 constexpr int kThreadsL = 128;
+constexpr int kRowL = kChunk + 1;   // per-thread window: j of the previous chunk's last angle + the 16 angles of this chunk
 
+// One thread per sample.  The sweep runs in fully unrolled 16-angle chunks exactly like K1u (no quadrature: 6 fp64
+// instructions per angle) and parks the chunk in a private shared-memory window; the probe points whose interval lies in
+// the window -- a contiguous range of the sorted list, the same for every thread -- are then interpolated from it.
 __global__ void __launch_bounds__(kThreadsL) loglike_kernel(const EvalParams p, const LoglikeParams lp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     MeasPoint* msm = reinterpret_cast<MeasPoint*>(smem_raw);                       // [m]
     int* seg = reinterpret_cast<int*>(msm + lp.m);                                 // [A]
+    double* win_all = reinterpret_cast<double*>(smem_raw + ((sizeof(MeasPoint) * lp.m + sizeof(int) * p.n_angles + 15) & ~size_t(15)));
     const int A = p.n_angles;
     for (int i = threadIdx.x; i < lp.m; i += kThreadsL) msm[i] = lp.meas[i];
     for (int i = threadIdx.x; i < A; i += kThreadsL) seg[i] = lp.seg_start[i];
     __syncthreads();
     const long long s = (long long)blockIdx.x * kThreadsL + threadIdx.x;
     if (s >= p.n) return;
+    double* win = win_all + threadIdx.x * kRowL;          // odd pitch (17 doubles): conflict-free across the warp
 
     double x_in[kNumInputs];
 #pragma unroll
@@ -1668,8 +1674,15 @@ __global__ void __launch_bounds__(kThreadsL) loglike_kernel(const EvalParams p, 
             beam_next_chunk(t2);
         }
     }
+    if (invalid) {          // constant row whatever else is NaN: zero amplitudes on a neutral recurrence, the fill as the floor
+        b1.amp = b2.amp = 0.0;
+        b1.ec = b1.rc = b1.gc = b1.q = b1.qk = b1.hh = 1.0;
+        b2.ec = b2.rc = b2.gc = b2.q = b2.qk = b2.hh = 1.0;
+        b1.x = b2.x = 0.0;
+        j_cex = kInvalidFill;
+    }
 
-    double ll = 0.0, j_prev = 0.0;
+    double ll = 0.0;
     double* pred = lp.y_pred ? lp.y_pred + s * (long long)lp.m : nullptr;
     for (int c = 0; c < n_chunks; ++c) {
         const int i0 = c * kChunk;
@@ -1678,26 +1691,26 @@ __global__ void __launch_bounds__(kThreadsL) loglike_kernel(const EvalParams p, 
             beam_restart(b2, i0);
         }
         double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec, r1 = b1.rc, r2 = b2.rc;
-        const int kcount = min(kChunk, A - i0);
-        for (int kk = 0; kk < kcount; ++kk) {
-            const int i = i0 + kk;
-            const double j = invalid ? kInvalidFill : (e1 + e2) + j_cex;
-            if (i > 0) {
-                const double dj = j - j_prev;
-                for (int q = seg[i - 1]; q < seg[i]; ++q) {        // warp-uniform trip count, broadcast loads
-                    const MeasPoint mp = msm[q];
-                    const double yh = fma(mp.w, dj, j_prev);         // linear interpolation on [alpha[i-1], alpha[i]]
-                    const double r = (mp.y - yh) * mp.inv_sigma;
-                    ll = fma(-0.5 * r, r, ll);
-                    if (pred) pred[mp.orig] = yh;
-                }
-            }
-            j_prev = j;
+        if (c != 0) win[0] = win[kChunk];                  // j of angle i0 - 1
+#pragma unroll
+        for (int kk = 0; kk < kChunk; ++kk) {              // angles >= A of the last chunk are computed but never read
+            win[kk + 1] = (e1 + e2) + j_cex;
             e1 *= r1; r1 *= b1.q;
             e2 *= r2; r2 *= b2.q;
         }
         beam_next_chunk(b1);
         beam_next_chunk(b2);
+        // intervals [lo, lo+1] with both ends in the window: lo = max(i0 - 1, 0) .. min(i0 + 15, A - 1) - 1
+        const int lo_first = max(i0 - 1, 0), hi_last = min(i0 + kChunk - 1, A - 1);
+        const int q0 = seg[lo_first], q1 = seg[hi_last];   // warp-uniform range of the sorted points
+        for (int q = q0; q < q1; ++q) {
+            const MeasPoint mp = msm[q];                    // broadcast loads
+            const double ja = win[mp.lo - i0 + 1], jb = win[mp.lo - i0 + 2];
+            const double yh = fma(mp.w, jb - ja, ja);       // linear interpolation on [alpha[lo], alpha[lo+1]]
+            const double r = (mp.y - yh) * mp.inv_sigma;
+            ll = fma(-0.5 * r, r, ll);
+            if (pred) pred[mp.orig] = yh;
+        }
     }
     if (lp.loglike) lp.loglike[s] = ll;
 }

@@ -17,6 +17,7 @@ def test_loglike_and_interpolation_match_oracle(n, n_angles, m, cuda_device):
     if n == 3000:                                   # mix in the edge rows (invalid samples, NaN rows, needle beams)
         e = edge_batch()
         b = {k: np.concatenate([e[k], b[k]]) for k in b}
+        b['c2'][40], b['c3'][40], b['c1'][40] = -15.0, -0.5, np.nan      # alpha1 <= 0 AND a NaN elsewhere: still the 1e-20 row
     theta = rng.uniform(-np.pi / 2, np.pi / 2, m)
     theta[0] = 0.0
     if m > 3:
