@@ -143,27 +143,29 @@ __device__ __forceinline__ void beam_init(BeamState& b, double h, double a, doub
     const double t = h / a;
     b.x = t * t;                           // profile(i) = exp(-x i^2)
     b.amp = amp;
-    b.q = exp(-2.0 * b.x);
-    b.qk = exp(-(2.0 * kChunk) * b.x);
-    b.hh = exp(-(2.0 * kChunk * kChunk) * b.x);
+    // three exps; q = exp(-2x) and hh = exp(-512x) are squares of two of them.  The extra rounding (1 ulp on a factor that
+    // is applied <= 16 times between exact re-anchorings) adds ~1.5e-14 to the recurrence's relative error (budget 1e-12).
     b.rc = exp(-b.x);
+    b.q = b.rc * b.rc;
+    b.qk = exp(-(2.0 * kChunk) * b.x);
     b.gc = exp(-double(kChunk * kChunk) * b.x);
+    b.hh = b.gc * b.gc;
     b.ec = 1.0;
 }
 // same for a sweep whose chunks start at angle index o + 16 c, o in {0, 1, 2, 3} per lane (quad-row store mode: the rows of
 // a warp start their 32-byte-aligned body at different angles).  One code path for every offset -- no divergence -- and
-// still five exps: the offset-dependent start values are small powers of u = exp(-x) and of qk = exp(-32 x)
+// still three exps: the offset-dependent start values are small powers of u = exp(-x) and of qk = exp(-32 x)
 // (<= 6 extra roundings, a constant ~5e-16 relative factor on the row).  `u` is returned for the lead elements.
 __device__ __forceinline__ double beam_init_offset(BeamState& b, double h, double a, double amp, int o) {
     const double t = h / a;
     b.x = t * t;
     b.amp = amp;
     const double u = exp(-b.x);
-    b.q = exp(-2.0 * b.x);
-    b.qk = exp(-(2.0 * kChunk) * b.x);
-    b.hh = exp(-(2.0 * kChunk * kChunk) * b.x);
-    const double g0 = exp(-double(kChunk * kChunk) * b.x);
     const double u2 = u * u, u4 = u2 * u2;
+    b.q = u2;
+    b.qk = exp(-(2.0 * kChunk) * b.x);
+    const double g0 = exp(-double(kChunk * kChunk) * b.x);
+    b.hh = g0 * g0;
     // E(o) = u^(o^2), E(o+1)/E(o) = u^(2o+1), E(o+16)/E(o) = g0 * qk^o
     b.ec = (o == 0) ? 1.0 : (o == 1) ? u : (o == 2) ? u4 : u4 * u4 * u;
     b.rc = (o == 0) ? u : (o == 1) ? u2 * u : (o == 2) ? u4 * u : u4 * u2 * u;
