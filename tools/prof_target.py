@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""ncu target: a few launches of ONE kernel family.  python tools/prof_target.py {k1u|k1v|k2|k2s|k3|k4|k5|k1r}"""
+"""ncu target: a few launches of ONE kernel family.  python tools/prof_target.py {k1u|k1q|k2|k2s|k3|k4|k5|k1w}
+(k1u: 1e6 x 200, (n, A) tensor stores; k1q: 1e6 x 91, quad-row tensor stores; k1w: 1e5 x 91 x 25 radii)"""
 import sys
 from pathlib import Path
 
@@ -18,7 +19,7 @@ def dev(b):
     return {k: torch.as_tensor(v, device='cuda:0') for k, v in b.items()}
 
 
-if what in ('k1u', 'k1v'):
+if what in ('k1u', 'k1q'):
     A = 200 if what == 'k1u' else 91
     call = PreparedCall(dev(spt100_batch(1_000_000, 1)), want_cathode=True, want_plume=True, sweep_radius=1.0, n_angles=A)
     for _ in range(3):
@@ -46,7 +47,7 @@ elif what in ('k4', 'k5'):
     z = comp.compress_inputs(d, torr=TORR)
     for _ in range(3):
         z = comp.compress_inputs(d, torr=TORR) if what == 'k4' else comp.reconstruct_field(z) * 0 + z
-elif what == 'k1r':
+elif what == 'k1w':
     call = PreparedCall(dev(spt100_batch(100_000, 1, c3_test_range=True)), want_cathode=False, want_plume=True,
                         sweep_radius=np.linspace(1.0, 1.2, 25), n_angles=91)
     for _ in range(3):
