@@ -413,3 +413,37 @@ def test_wide_range_fuzz_against_oracle(n_angles, seed, cuda_device):
             out[key] = np.where(sub, np.nan, out[key])
             gmode[key] = np.where(sub, np.nan, gold[key])
         _compare(out, gmode, b, torr, np.array([1.0]), f'fuzz a{n_angles} {mode}')
+
+
+@pytest.mark.parametrize('n,n_angles,radii', [(1001, 91, None), (4099, 93, None), (777, 66, None), (1000, 200, None),
+                                              (333, 51, None), (130, 255, None), (403, 91, 25), (64, 100, 3)])
+def test_no_store_outside_the_output(n, n_angles, radii, cuda_device):
+    """Guard bands around every output buffer stay untouched (tensor-store boxes, boundary-sector writes, bulk copies and
+    the late-fix rewrite must never reach past the rows they own), for all kernel variants."""
+    import torch
+    from hallthrusterpem_b200.engine import PreparedCall
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    from oracle.make_golden import edge_batch
+    b = spt100_batch(n, n + n_angles)
+    e = edge_batch()
+    k = min(len(e['P_b']), n // 4)
+    b = {key: np.concatenate([b[key][:7], e[key][:k], b[key][7:n - k]]) for key in b}
+    d = {key: torch.as_tensor(v, device='cuda:0') for key, v in b.items()}
+    sweep = 1.0 if radii is None else np.linspace(1.0, 1.4, radii)
+    R = 1 if radii is None else radii
+    guard = 4096                                           # elements, keeps the 32-byte alignment of the payload
+    sentinel = -7.25
+    for mode in ('default', 'no_quad', 'lanes4', 'lanes1', 'direct'):
+        call = PreparedCall(d, want_cathode=True, want_plume=True, sweep_radius=sweep, n_angles=n_angles, extras=True, **MODES[mode])
+        sizes = {'j_ion': n * n_angles * R, 'div_angle': n * R, 'T_c': n * R, 'cos_div': n * R, 'V_cc': n}
+        backing = {}
+        for name, size in sizes.items():
+            buf = torch.full((size + 2 * guard,), sentinel, dtype=torch.float64, device='cuda:0')
+            backing[name] = buf
+            setattr(call.out, name, buf[guard:].data_ptr())
+        call.run()
+        torch.cuda.synchronize()
+        for name, size in sizes.items():
+            buf = backing[name]
+            assert bool((buf[:guard] == sentinel).all()) and bool((buf[guard + size:] == sentinel).all()), (mode, name)
+            assert not bool((buf[guard:guard + size] == sentinel).any()), (mode, name, 'payload not fully written')
