@@ -65,6 +65,11 @@ struct Workspace {
     size_t j_cap = 0;  // elements
     cudaStream_t s_compute = nullptr, s_copy = nullptr, s_h2d = nullptr;
     std::vector<cudaEvent_t> events, h2d_events;
+    // small-batch path of hpem_eval_host: ONE packed H2D and ONE packed D2H through pinned staging buffers
+    unsigned char* h_stage_in = nullptr;
+    unsigned char* h_stage_out = nullptr;
+    unsigned char* d_pack_in = nullptr;
+    unsigned char* d_pack_out = nullptr;
     double* d_partials = nullptr;  // K2 per-block partial vectors
     size_t partials_cap = 0;
     double* d_partial_minmax = nullptr;
@@ -471,6 +476,10 @@ int hpem_grid_destroy(hpem_grid* g) {
     for (auto& p : ws.d_small) if (p) cudaFree(p);
     if (ws.d_invalid) cudaFree(ws.d_invalid);
     if (ws.d_j) cudaFree(ws.d_j);
+    if (ws.h_stage_in) cudaFreeHost(ws.h_stage_in);
+    if (ws.h_stage_out) cudaFreeHost(ws.h_stage_out);
+    if (ws.d_pack_in) cudaFree(ws.d_pack_in);
+    if (ws.d_pack_out) cudaFree(ws.d_pack_out);
     if (ws.d_partials) cudaFree(ws.d_partials);
     if (ws.d_partial_minmax) cudaFree(ws.d_partial_minmax);
     for (auto e : ws.events) cudaEventDestroy(e);
@@ -529,6 +538,68 @@ int hpem_eval_host(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_ou
     if (plume) for (int k : kPlumeInputs) need[k] = true;
     if (out->T_c) need[HPEM_IN_T] = true;
 
+    // ---- small batches (what amisc passes outside of Monte-Carlo runs, down to one sample per call): the per-array
+    // cudaMemcpy calls of the pipeline below cost more than the whole evaluation, so the needed inputs are packed into
+    // one pinned staging buffer (ONE H2D), the per-sample outputs come back packed (ONE D2H), one stream, one sync.
+    {
+        constexpr size_t kPackBytes = size_t(2) << 20;
+        int n_arrays = 0;
+        for (int k = 0; k < HPEM_N_INPUTS; ++k) n_arrays += (need[k] && in->ptr[k]) ? 1 : 0;
+        const size_t in_bytes = size_t(n_arrays) * n * sizeof(double);
+        const size_t per_r = size_t(n) * R * sizeof(double);
+        const size_t out_bytes = (out->V_cc ? size_t(n) * 8 : 0) + (out->div_angle ? per_r : 0) + (out->T_c ? per_r : 0) +
+                                 (out->cos_div ? per_r : 0) + (out->invalid ? ((size_t(n) + 7) & ~size_t(7)) : 0);
+        const size_t j_bytes = out->j_ion ? size_t(n) * A * R * sizeof(double) : 0;
+        if (in_bytes <= kPackBytes && out_bytes <= kPackBytes && j_bytes <= (size_t(64) << 20)) {
+            if (!ws.h_stage_in) {
+                HPEM_CUDA(cudaHostAlloc((void**)&ws.h_stage_in, kPackBytes, cudaHostAllocDefault));
+                HPEM_CUDA(cudaHostAlloc((void**)&ws.h_stage_out, kPackBytes, cudaHostAllocDefault));
+                HPEM_CUDA(cudaMalloc((void**)&ws.d_pack_in, kPackBytes));
+                HPEM_CUDA(cudaMalloc((void**)&ws.d_pack_out, kPackBytes));
+            }
+            hpem_inputs din = *in;
+            size_t off = 0;
+            for (int k = 0; k < HPEM_N_INPUTS; ++k) {
+                din.ptr[k] = nullptr;
+                if (!need[k] || !in->ptr[k]) continue;
+                std::memcpy(ws.h_stage_in + off, in->ptr[k], size_t(n) * sizeof(double));
+                din.ptr[k] = reinterpret_cast<const double*>(ws.d_pack_in + off);
+                off += size_t(n) * sizeof(double);
+            }
+            if (off) HPEM_CUDA(cudaMemcpyAsync(ws.d_pack_in, ws.h_stage_in, off, cudaMemcpyHostToDevice, ws.s_compute));
+            hpem_outputs dout = {};
+            size_t o = 0;
+            auto take = [&](bool wanted, size_t bytes) -> unsigned char* {
+                if (!wanted) return nullptr;
+                unsigned char* ptr = ws.d_pack_out + o;
+                o += bytes;
+                return ptr;
+            };
+            dout.V_cc = reinterpret_cast<double*>(take(out->V_cc != nullptr, size_t(n) * 8));
+            dout.div_angle = reinterpret_cast<double*>(take(out->div_angle != nullptr, per_r));
+            dout.T_c = reinterpret_cast<double*>(take(out->T_c != nullptr, per_r));
+            dout.cos_div = reinterpret_cast<double*>(take(out->cos_div != nullptr, per_r));
+            dout.invalid = take(out->invalid != nullptr, (size_t(n) + 7) & ~size_t(7));
+            if (out->j_ion) {
+                rc = grow(ws.d_j, ws.j_cap, (size_t)(n * A * R));
+                if (rc != HPEM_OK) return rc;
+                dout.j_ion = ws.d_j;
+            }
+            rc = launch_range(*g, din, dout, 0, n, torr_2_pa, plume, flags, ws.s_compute);
+            if (rc != HPEM_OK) return rc;
+            if (o) HPEM_CUDA(cudaMemcpyAsync(ws.h_stage_out, ws.d_pack_out, o, cudaMemcpyDeviceToHost, ws.s_compute));
+            if (out->j_ion) HPEM_CUDA(cudaMemcpyAsync(out->j_ion, ws.d_j, j_bytes, cudaMemcpyDeviceToHost, ws.s_compute));
+            HPEM_CUDA(cudaStreamSynchronize(ws.s_compute));
+            const unsigned char* hs = ws.h_stage_out;
+            if (out->V_cc) { std::memcpy(out->V_cc, hs, size_t(n) * 8); hs += size_t(n) * 8; }
+            if (out->div_angle) { std::memcpy(out->div_angle, hs, per_r); hs += per_r; }
+            if (out->T_c) { std::memcpy(out->T_c, hs, per_r); hs += per_r; }
+            if (out->cos_div) { std::memcpy(out->cos_div, hs, per_r); hs += per_r; }
+            if (out->invalid) std::memcpy(out->invalid, hs, size_t(n));
+            return HPEM_OK;
+        }
+    }
+
     // super-batches bound the device footprint of j_ion (default cap 16 GiB of the 180 GB HBM)
     const int64_t row_elems = A * R;
     const int64_t cap_elems = ((int64_t)16 << 30) / 8;
@@ -577,40 +648,54 @@ int hpem_eval_host(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_ou
             dout.j_ion = ws.d_j;
         }
 
-        // H2D of the per-sample inputs in segments of 8 chunks on their own stream: the upload of segment k+1 overlaps
-        // the kernels and the D2H of segment k (PCIe is full duplex)
-        const int64_t seg = chunk * 8;
-        const int64_t n_seg = (nb + seg - 1) / seg;
+        // H2D of the per-sample inputs in segments (the first one chunk long, then 8 chunks each) on their own stream.  The
+        // upload of segment k+1 is ISSUED after the kernels and D2H copies of segment k: with pinned inputs the order does
+        // not matter (everything is asynchronous, PCIe is full duplex), but a cudaMemcpyAsync from PAGEABLE memory -- what
+        // amisc passes -- blocks the host while the driver stages it, and issued up front those 120 B per sample delayed the
+        // first kernel by the whole upload (40 ms instead of 32 ms per 1e6 x 200 batch).
+        const int64_t n_chunks = (nb + chunk - 1) / chunk;
+        const int64_t n_seg = 1 + (std::max<int64_t>(n_chunks - 1, 0) + 7) / 8;
+        auto seg_first_chunk = [](int64_t sg) { return sg == 0 ? (int64_t)0 : 1 + (sg - 1) * 8; };
         while ((int64_t)ws.h2d_events.size() < n_seg) {
             cudaEvent_t e;
             HPEM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             ws.h2d_events.push_back(e);
         }
-        for (int64_t sg = 0; sg < n_seg; ++sg) {
-            const int64_t first = sg * seg, count = std::min(seg, nb - first);
+        while ((int64_t)ws.events.size() < n_chunks) {
+            cudaEvent_t e;
+            HPEM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ws.events.push_back(e);
+        }
+        auto upload = [&](int64_t sg) -> int {
+            const int64_t c0 = seg_first_chunk(sg), c1 = std::min(n_chunks, seg_first_chunk(sg + 1));
+            const int64_t first = c0 * chunk, count = std::min(nb, c1 * chunk) - first;
             for (int k = 0; k < HPEM_N_INPUTS; ++k) {
                 if (!din.ptr[k]) continue;
                 HPEM_CUDA(cudaMemcpyAsync(ws.d_in[k] + first, in->ptr[k] + b0 + first, (size_t)count * sizeof(double),
                                           cudaMemcpyHostToDevice, ws.s_h2d));
             }
             HPEM_CUDA(cudaEventRecord(ws.h2d_events[sg], ws.s_h2d));
-        }
-        const int64_t n_chunks = (nb + chunk - 1) / chunk;
-        while ((int64_t)ws.events.size() < n_chunks) {
-            cudaEvent_t e;
-            HPEM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            ws.events.push_back(e);
-        }
-        for (int64_t c = 0; c < n_chunks; ++c) {
-            const int64_t first = c * chunk, count = std::min(chunk, nb - first);
-            if (c % 8 == 0) HPEM_CUDA(cudaStreamWaitEvent(ws.s_compute, ws.h2d_events[c / 8], 0));
-            rc = launch_range(*g, din, dout, first, count, torr_2_pa, plume, flags, ws.s_compute);
-            if (rc != HPEM_OK) return rc;
-            if (out->j_ion) {
-                HPEM_CUDA(cudaEventRecord(ws.events[c], ws.s_compute));
-                HPEM_CUDA(cudaStreamWaitEvent(ws.s_copy, ws.events[c], 0));
-                HPEM_CUDA(cudaMemcpyAsync(out->j_ion + (b0 + first) * row_elems, ws.d_j + first * row_elems,
-                                          (size_t)(count * row_elems) * sizeof(double), cudaMemcpyDeviceToHost, ws.s_copy));
+            return HPEM_OK;
+        };
+        rc = upload(0);
+        if (rc != HPEM_OK) return rc;
+        for (int64_t sg = 0; sg < n_seg; ++sg) {
+            const int64_t c0 = seg_first_chunk(sg), c1 = std::min(n_chunks, seg_first_chunk(sg + 1));
+            HPEM_CUDA(cudaStreamWaitEvent(ws.s_compute, ws.h2d_events[sg], 0));
+            for (int64_t c = c0; c < c1; ++c) {
+                const int64_t first = c * chunk, count = std::min(chunk, nb - first);
+                rc = launch_range(*g, din, dout, first, count, torr_2_pa, plume, flags, ws.s_compute);
+                if (rc != HPEM_OK) return rc;
+                if (out->j_ion) {
+                    HPEM_CUDA(cudaEventRecord(ws.events[c], ws.s_compute));
+                    HPEM_CUDA(cudaStreamWaitEvent(ws.s_copy, ws.events[c], 0));
+                    HPEM_CUDA(cudaMemcpyAsync(out->j_ion + (b0 + first) * row_elems, ws.d_j + first * row_elems,
+                                              (size_t)(count * row_elems) * sizeof(double), cudaMemcpyDeviceToHost, ws.s_copy));
+                }
+            }
+            if (sg + 1 < n_seg) {
+                rc = upload(sg + 1);
+                if (rc != HPEM_OK) return rc;
             }
         }
         for (int q = 0; q < 4; ++q) {

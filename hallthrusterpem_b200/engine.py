@@ -29,12 +29,20 @@ used historically.  If `pem_core` is importable its value is used instead (see `
 _PIN_THRESHOLD_BYTES = 1 << 20
 
 
+_torr_cache: float | None = None
+
+
 def torr_2_pa() -> float:
-    try:  # the real dependency, when present, is authoritative
-        from pem_core.constants import TORR_2_PA  # type: ignore
-        return float(TORR_2_PA)
-    except Exception:
-        return DEFAULT_TORR_2_PA
+    """pem_core's constant when `pem_core` is importable (the real dependency is authoritative), else 133.322.
+    Resolved once: a failing import costs ~100 us per attempt, more than a small batch takes on the GPU."""
+    global _torr_cache
+    if _torr_cache is None:
+        try:
+            from pem_core.constants import TORR_2_PA  # type: ignore
+            _torr_cache = float(TORR_2_PA)
+        except Exception:
+            _torr_cache = DEFAULT_TORR_2_PA
+    return _torr_cache
 
 
 def _torch():
@@ -103,64 +111,130 @@ def get_grid(device: int, n_angles: int, radii: np.ndarray) -> GridHandle:
 # ----------------------------------------------------------------------------------------------
 # input marshalling
 # ----------------------------------------------------------------------------------------------
+_INPUT_INDEX = {name: k for k, name in enumerate(_lib.INPUT_NAMES)}
+
+
 class _Batch:
-    """Broadcast the named inputs to a common loop shape and build the hpem_inputs struct."""
+    """Broadcast the named inputs to a common loop shape and build the hpem_inputs struct.
+    (Kept lean: for the small batches amisc often passes, this marshalling is most of the call's latency.)"""
 
     def __init__(self, inputs: dict, names: tuple[str, ...], optional: tuple[str, ...] = ()):
         vals = {}
         for name in names:
             vals[name] = inputs[name]                     # KeyError for a missing key, like the reference
         for name in optional:
-            if inputs.get(name, None) is not None:
-                vals[name] = inputs[name]
-        self.on_device = any(_is_torch_tensor(v) and v.is_cuda for v in vals.values())
+            v = inputs.get(name, None)
+            if v is not None:
+                vals[name] = v
+        # classify once: (value, is_torch, shape)
+        info = {}
+        devs = set()
+        shapes = set()
+        for name, v in vals.items():
+            is_t = _is_torch_tensor(v)
+            shape = tuple(v.shape) if (is_t or hasattr(v, 'shape')) else ()
+            if is_t and v.is_cuda:
+                devs.add(v.device.index)
+            info[name] = (v, is_t, shape)
+            shapes.add(shape)
+        self.on_device = bool(devs)
         self.device_index = None
         if self.on_device:
-            devs = {v.device.index for v in vals.values() if _is_torch_tensor(v) and v.is_cuda}
             if len(devs) != 1:
                 raise ValueError(f'inputs live on several CUDA devices: {sorted(devs)}')
             self.device_index = devs.pop()
-        shapes = [tuple(v.shape) if hasattr(v, 'shape') else () for v in vals.values()]
-        self.loop_shape = tuple(np.broadcast_shapes(*shapes)) if shapes else ()
+        if len(shapes) == 1:
+            self.loop_shape = next(iter(shapes))
+        else:
+            self.loop_shape = tuple(np.broadcast_shapes(*shapes)) if shapes else ()
         self.out_shape = self.loop_shape if len(self.loop_shape) > 0 else (1,)   # np.atleast_1d (plume.py:59)
-        self.n = int(np.prod(self.out_shape, dtype=np.int64))
-        self.struct = _lib.HpemInputs()
-        self._keep = []                                   # keep converted buffers alive during the call
-        for name, v in vals.items():
-            k = _lib.INPUT_NAMES.index(name)
-            size = int(np.prod(v.shape, dtype=np.int64)) if hasattr(v, 'shape') else 1
+        n = 1
+        for d in self.out_shape:
+            n *= int(d)
+        self.n = n
+        self.struct = struct = _lib.HpemInputs()
+        self._keep = keep = []                            # keep converted buffers alive during the call
+        out_shape = self.out_shape
+        for name, (v, is_t, shape) in info.items():
+            k = _INPUT_INDEX[name]
+            size = 1
+            for d in shape:
+                size *= int(d)
             if size == 1:                                 # NumPy scalar broadcasting (test_plume.py:67-77)
-                self.struct.ptr[k] = None
-                self.struct.scalar[k] = float(v.reshape(-1)[0]) if hasattr(v, 'shape') else float(v)
+                struct.ptr[k] = None
+                struct.scalar[k] = float(v.reshape(-1)[0]) if shape != () or hasattr(v, 'reshape') else float(v)
                 continue
             if self.on_device:
                 torch = _torch()
-                t = v if _is_torch_tensor(v) else torch.as_tensor(np.asarray(v, dtype=np.float64))
-                t = t.to(device=f'cuda:{self.device_index}', dtype=torch.float64)
-                if tuple(t.shape) != self.out_shape:
-                    t = t.broadcast_to(self.out_shape)
-                t = t.contiguous()
-                self._keep.append(t)
-                self.struct.ptr[k] = t.data_ptr()
+                t = v if is_t else torch.as_tensor(np.asarray(v, dtype=np.float64))
+                if t.dtype != torch.float64 or not t.is_cuda or t.device.index != self.device_index:
+                    t = t.to(device=f'cuda:{self.device_index}', dtype=torch.float64)
+                if shape != out_shape:
+                    t = t.broadcast_to(out_shape)
+                if not t.is_contiguous():
+                    t = t.contiguous()
+                keep.append(t)
+                struct.ptr[k] = t.data_ptr()
             else:
-                a = v.detach().cpu().numpy() if _is_torch_tensor(v) else np.asarray(v)
-                a = np.asarray(a, dtype=np.float64)
-                if a.shape != self.out_shape:
-                    a = np.broadcast_to(a, self.out_shape)
-                a = np.ascontiguousarray(a)
-                self._keep.append(a)
-                self.struct.ptr[k] = a.ctypes.data
+                a = v.detach().cpu().numpy() if is_t else v
+                if not (type(a) is np.ndarray and a.dtype == np.float64 and a.flags.c_contiguous and shape == out_shape):
+                    a = np.asarray(a, dtype=np.float64)
+                    if a.shape != out_shape:
+                        a = np.broadcast_to(a, out_shape)
+                    a = np.ascontiguousarray(a)
+                keep.append(a)
+                struct.ptr[k] = a.__array_interface__['data'][0]
         self.present = set(vals)
 
 
+class _PinnedPool:
+    """Free-list of page-locked host buffers behind the NumPy outputs of the host path.
+
+    Pinning memory costs about as much as copying into it (cudaHostAlloc: ~15 us per MB), so the buffers must be reused
+    across calls.  torch's caching host allocator does that when the previous result is dropped BEFORE the next call, but
+    in the usual loop `out = current_density(inputs)` the previous result is still alive while the next one is allocated,
+    and every call then pins fresh memory (measured: 11 ms per call for a 728 MB `j_ion`).  Here a buffer returns to the
+    free-list when the last NumPy view of it dies (weakref.finalize on the root array), so that loop settles on two
+    alternating buffers."""
+
+    def __init__(self, max_cached_bytes: int = 8 << 30):
+        self._free: dict[int, list] = {}
+        self._cached = 0
+        self._max = max_cached_bytes
+        self._lock = threading.Lock()
+
+    def _release(self, nbytes: int, tensor) -> None:
+        with self._lock:
+            if self._cached + nbytes <= self._max:
+                self._free.setdefault(nbytes, []).append(tensor)
+                self._cached += nbytes
+
+    def take(self, shape: tuple[int, ...], dtype) -> np.ndarray:
+        import weakref
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+        with self._lock:
+            lst = self._free.get(nbytes)
+            tensor = lst.pop() if lst else None
+            if tensor is not None:
+                self._cached -= nbytes
+        if tensor is None:
+            torch = _torch()
+            tensor = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        root = tensor.numpy()                      # every view handed out collapses its `.base` chain onto this array
+        weakref.finalize(root, self._release, nbytes, tensor)
+        return root.view(dt).reshape(shape)
+
+
+_pinned_pool = _PinnedPool()
+
+
 def _alloc_host(shape: tuple[int, ...], dtype=np.float64) -> np.ndarray:
-    """Host output buffer; large ones are page-locked (through torch's caching host allocator, so repeated
-    calls reuse the registration) and the D2H copy DMAs straight into the array that is returned."""
+    """Host output buffer; large ones are page-locked (pooled, see _PinnedPool) and the D2H copy DMAs straight into the
+    array that is returned."""
     nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
     if nbytes >= _PIN_THRESHOLD_BYTES:
-        torch = _torch()
-        tdtype = torch.float64 if np.dtype(dtype) == np.float64 else torch.uint8
-        return torch.empty(shape, dtype=tdtype, pin_memory=True).numpy()
+        return _pinned_pool.take(shape, dtype)
     return np.empty(shape, dtype=dtype)
 
 

@@ -256,3 +256,37 @@ def test_pem_to_xarray_layout_matches_reference_text():
     single = pem_to_xarray(ops, {**out, 'j_ion': out['j_ion'][..., 0], 'T_c': out['T_c'][:, 0]}, 1.0, use_corrected_thrust=False)
     assert np.asarray(single[0]['data']['ion current density']['val'].values).shape == (1, A)
     assert float(np.asarray(single[1]['data']['thrust']['val'].values)) == out['T'][1]
+
+
+def test_pinned_output_pool_reuses_buffers(monkeypatch):
+    """engine._PinnedPool: a buffer returns to the free-list only when its last NumPy view dies; the usual loop
+    `out = f(x)` (previous result alive during the next call) settles on two buffers instead of pinning fresh memory."""
+    import gc
+    import torch
+    from hallthrusterpem_b200 import engine
+    real_empty = torch.empty
+    allocations = []
+
+    def fake_empty(n, dtype=None, pin_memory=False):
+        assert pin_memory
+        allocations.append(n)
+        return real_empty(n, dtype=dtype)
+
+    monkeypatch.setattr(torch, 'empty', fake_empty)
+    pool = engine._PinnedPool(max_cached_bytes=10 * 1000 * 91 * 8)
+    a = pool.take((1000, 91), np.float64)
+    assert a.shape == (1000, 91) and a.dtype == np.float64 and a.flags.c_contiguous
+    view = a[10:20]
+    del a
+    gc.collect()
+    assert pool._cached == 0                                   # a view is still alive: the buffer must not be recycled
+    pool.take((1000, 91), np.float64)
+    del view
+    gc.collect()
+    assert len(allocations) == 2
+    out = None
+    for _ in range(10):
+        out = pool.take((1000, 91), np.float64)                # noqa: F841  previous result alive while the next is allocated
+    assert len(allocations) <= 4
+    m = pool.take((7, 3), np.uint8)
+    assert m.shape == (7, 3) and m.dtype == np.uint8
