@@ -390,21 +390,24 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
                     if ((c % kTmaCB) == kTmaCB - 1 || last_chunk) {
                         fence_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
-                            const int c_first = c - (c % kTmaCB);
-                            const bool whole = c_first + kTmaCB <= A_sweep / kChunk;
-                            if (QUAD) {
-#pragma unroll
-                                for (int f = 0; f < 4; ++f) {
-                                    const uint32_t src = smem_u32(group_buf + f * (kTmaCB * 1024));
-                                    if (whole) {
-                                        tma_issue_3d(&maps.m3[f], src, 0, tma_row0, c_first);
-                                    } else {
-                                        for (int cc = c_first; cc <= c; ++cc)
-                                            tma_issue_2d(&maps.m2[f], src + (cc - c_first) * 1024, cc * kChunk, tma_row0);
-                                    }
+                        const int c_first = c - (c % kTmaCB);
+                        const bool whole = c_first + kTmaCB <= A_sweep / kChunk;
+                        if (QUAD) {
+                            // lanes 0-3 ship the four phases in parallel (one instruction sequence instead of four);
+                            // bulk-group bookkeeping is per thread, so each of them commits and waits for its own ops
+                            if (lane < 4) {
+                                const uint32_t src = smem_u32(group_buf + lane * (kTmaCB * 1024));
+                                if (whole) {
+                                    tma_issue_3d(&maps.m3[lane], src, 0, tma_row0, c_first);
+                                } else {
+                                    for (int cc = c_first; cc <= c; ++cc)
+                                        tma_issue_2d(&maps.m2[lane], src + (cc - c_first) * 1024, cc * kChunk, tma_row0);
                                 }
-                            } else if (whole) {
+                                tma_commit();
+                                tma_wait_read<NBUF - 1>();   // the buffer the next group goes into is free again
+                            }
+                        } else if (lane == 0) {
+                            if (whole) {
                                 tma_issue_3d(&maps.m3[0], smem_u32(group_buf), 0, tma_row0, c_first);
                             } else {
                                 for (int cc = c_first; cc <= c; ++cc)
@@ -449,15 +452,17 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
             // write the row boundaries: boundary r = tail of row r + lead of row r+1, contiguous in memory and a whole
             // number of sectors; 8 lanes per boundary, so each sector is written by adjacent lanes of one instruction
             __syncwarp();
+            // element e = 32 it + lane of the [32 boundaries][8 slots] buffer: boundary r = 4 it + lane / 8, slot = lane % 8,
+            // so the phase of row r -- and with it tail and count -- is a per-lane constant
+            const int f = lane >> 3, slot = lane & 7;
+            const int t_r = p.q_tail[f];
+            const bool slot_ok = slot < t_r + p.q_lead[(f + 1) & 3];
+            double* gp = p.j_ion + (warp_s0 + f + 1) * (long long)A - t_r + slot;
+            const double* bp = bsec + lane;
 #pragma unroll
             for (int it = 0; it < kBsecSlots; ++it) {
-                const int e = it * 32 + lane;
-                const int r = e >> 3, slot = e & 7;
-                const int f = r & 3;
-                const int t_r = p.q_tail[f];
-                const int cnt = t_r + p.q_lead[(f + 1) & 3];
-                if (slot < cnt && warp_s0 + r < p.n)   // n % 4 == 0: row r+1 exists whenever its lead is non-empty
-                    __stcs(p.j_ion + (warp_s0 + r + 1) * (long long)A - t_r + slot, bsec[r * kBsecSlots + slot]);
+                if (slot_ok && warp_s0 + 4 * it + f < p.n) __stcs(gp, bp[it * 32]);   // n % 4 == 0: row r+1 exists whenever its lead is non-empty
+                gp += 4 * (long long)A;
             }
         }
     }
@@ -478,10 +483,11 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
     // rare: a non-positive j_ion found after earlier chunks were already written -> the row is overwritten below
     const bool late_fix = STORE_J && __any_sync(0xffffffffu, bad && !known_invalid);
     if (STORE_J && (USE_TMA || ROWS)) {
+        const bool issuer = QUAD ? lane < 4 : lane == 0;
         if (late_fix) {            // order the TMA (async proxy) writes before the generic-proxy rewrite
-            if (lane == 0) tma_wait_all();
+            if (issuer) tma_wait_all();
             fence_async_all();
-        } else if (lane == 0) {
+        } else if (issuer) {
             tma_wait_read<0>();    // the staging tiles must outlive the TMA reads
         }
         __syncwarp();
