@@ -1,16 +1,22 @@
 // hpem_kernels.cuh -- sm_100a kernels for the fused cathode + plume sample batch.
 //
-// K1u  eval_uniform_kernel : one THREAD per sample, uniform angle grid, single radius.
+// K1u  eval_uniform_kernel : one THREAD per sample, uniform angle grid, single radius (the default path).
 //        The two Gaussian beam profiles exp(-(i h / a)^2), i = 0..A-1, are advanced with a two-term
 //        multiplicative recurrence (e *= r; r *= q) restarted hierarchically, so the per-(sample, angle)
-//        cost is 4 DMUL + 2 DADD + 2 DFMA + 1 DSETP instead of two fp64 exp() calls (~40 fp64-pipe ops).
+//        cost is 4 DMUL + 2 DADD + 2 DFMA (+1 DSETP) instead of two fp64 exp() calls (~40 fp64-pipe ops).
 //        The kernel is then bound by the j_ion store stream (8 B per evaluation) -> HBM roofline.
-//        The warp's 32 samples x 16 angles are transposed through a private shared-memory tile so
-//        the global stores are full 128-byte row segments (streaming, evict-first).
+//        j_ion leaves through shared-memory staging and TMA tensor stores that always cover whole 32-byte
+//        sectors: (n, A) boxes when rows are sector-aligned (kStoreTma), the quad-row view otherwise
+//        (kStoreQuad); whole-row bulk copies (kStoreRows) and plain stores (kStoreStg) are the fallbacks.
 //        Quadrature sums are thread-local FMAs against weights broadcast from shared memory.
+// K1v  eval_lanes4_kernel  : four lanes per sample in the sweep, whole rows per 1-D bulk store.
+// K1w  eval_radii_stream_kernel / K1r eval_multi_radius_kernel : several sweep radii.
 // K1d  eval_direct_kernel  : one WARP per sample, any angle grid, any number of radii; evaluates
 //        the reference's expressions in the reference's operation order (divide, square, negate, exp);
 //        warp-shuffle reductions for the two Simpson sums.  Fallback + independent cross-check.
+// K2   moments_kernel      : reduce-only Monte-Carlo pass (moments + histograms), optional on-device sampling.
+// K3   loglike_kernel      : interpolation to probe angles + Gaussian log-likelihood.
+// (K4/K5, the SVD compression of j_ion, live in hpem_compress.cuh.)
 //
 // Reference lines reproduced: plume.py:95-127,136-140 (per angle / per sample epilogue),
 // cathode.py:26-37 and plume.py:40-85 via hpem_device.cuh.
