@@ -88,3 +88,20 @@ def test_oracle_properties():
     assert o['_invalid'][0] and np.all(o['j_ion'] == 1e-20) and np.isfinite(o['div_angle'][0])
     # scalar inputs -> (1, 91), (1,), object coords of shape (1,)
     assert o['j_ion'].shape == (1, 91) and o['div_angle'].shape == (1,) and o['j_ion_coords'].shape == (1,)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='reference sources not present (GPU box)')
+def test_drop_in_signatures_match_the_reference():
+    """Same callable names, same positional parameters with the same defaults; every extra parameter of the drop-in is
+    keyword-only with a default, so any call that is valid for the reference is valid for the drop-in."""
+    import inspect
+    from hallthrusterpem_b200.models import cathode_coupling, current_density
+    ref_plume, ref_cathode, _ = ref_import.load()
+    for ours, ref in ((current_density, ref_plume), (cathode_coupling, ref_cathode)):
+        assert ours.__name__ == ref.__name__
+        po, pr = inspect.signature(ours).parameters, inspect.signature(ref).parameters
+        assert list(po)[:len(pr)] == list(pr)
+        for name, prm in pr.items():
+            assert po[name].kind == prm.kind and po[name].default == prm.default
+        for name in list(po)[len(pr):]:
+            assert po[name].kind is inspect.Parameter.KEYWORD_ONLY and po[name].default is not inspect.Parameter.empty
