@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -602,10 +603,18 @@ int hpem_eval_host(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_ou
 
     // super-batches bound the device footprint of j_ion (default cap 16 GiB of the 180 GB HBM)
     const int64_t row_elems = A * R;
-    const int64_t cap_elems = ((int64_t)16 << 30) / 8;
-    const int64_t batch = out->j_ion ? std::max<int64_t>(1, std::min<int64_t>(n, cap_elems / row_elems)) : n;
+    // (HPEM_HOST_BATCH_BYTES / HPEM_HOST_CHUNK_BYTES override the two sizes: tests drive the multi-batch pipeline with them)
+    auto env_bytes = [](const char* name, int64_t dflt) {
+        const char* v = std::getenv(name);
+        const long long x = v ? std::atoll(v) : 0;
+        return x > 0 ? (int64_t)x : dflt;
+    };
+    const int64_t cap_elems = env_bytes("HPEM_HOST_BATCH_BYTES", (int64_t)16 << 30) / 8;
+    // (a multiple of 64 samples: every launch then sees a sample at the same position modulo 4 / 32 as a single launch over
+    //  the whole batch would, so the quad-row kernel -- whose rounding depends on a row's phase -- gives identical bits)
+    const int64_t batch = out->j_ion ? std::min<int64_t>(n, std::max<int64_t>(64, cap_elems / row_elems / 64 * 64)) : n;
     // D2H chunks of ~32 MiB so the copy engine starts as soon as the first rows exist
-    const int64_t chunk = out->j_ion ? (std::max<int64_t>(1024, ((int64_t)32 << 20) / (row_elems * 8)) + 63) / 64 * 64 : batch;
+    const int64_t chunk = out->j_ion ? (std::max<int64_t>(1024, env_bytes("HPEM_HOST_CHUNK_BYTES", (int64_t)32 << 20) / (row_elems * 8)) + 63) / 64 * 64 : batch;
 
     for (int64_t b0 = 0; b0 < n; b0 += batch) {
         const int64_t nb = std::min(batch, n - b0);

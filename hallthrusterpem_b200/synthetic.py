@@ -57,7 +57,17 @@ def h9_sweep_batch(n: int, seed: int = BASE_SEED + 3, with_thrust: bool = True) 
 
 
 def shard_bounds(n_total: int, world_size: int, rank: int) -> tuple[int, int]:
-    """Contiguous sample range [lo, hi) owned by `rank`."""
-    base, rem = divmod(n_total, world_size)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+    """Contiguous sample range [lo, hi) owned by `rank`, balanced to within one sample -- or, for
+    shards of 1024 samples and more, to within 64: interior boundaries are then multiples of 64 samples, so a sample sits
+    at the same position modulo 4 in its shard as in the unsharded batch, which keeps the materialised outputs
+    bit-identical to a single-GPU run (the quad-row kernel's rounding depends on that position)."""
+    align = 64 if n_total // max(world_size, 1) >= 1024 else 1
+
+    def edge(k: int) -> int:
+        if k <= 0:
+            return 0
+        if k >= world_size:
+            return n_total
+        base, rem = divmod(n_total, world_size)
+        return (k * base + min(k, rem)) // align * align
+    return edge(rank), edge(rank + 1)

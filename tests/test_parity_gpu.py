@@ -447,3 +447,23 @@ def test_no_store_outside_the_output(n, n_angles, radii, cuda_device):
             buf = backing[name]
             assert bool((buf[:guard] == sentinel).all()) and bool((buf[guard + size:] == sentinel).all()), (mode, name)
             assert not bool((buf[guard:guard + size] == sentinel).any()), (mode, name, 'payload not fully written')
+
+
+@pytest.mark.parametrize('n_angles', [91, 200, 66])
+def test_host_pipeline_many_batches_and_chunks(n_angles, cuda_device, monkeypatch):
+    """hpem_eval_host with its two sizes shrunk (super-batch 40 MB, chunk 1 MB): several super-batches whose first sample is
+    not a multiple of 4 or 64, dozens of chunks per batch, pageable and pinned inputs -- bit-identical to the device path (batches are multiples of 64 samples, so every row keeps
+    the phase it has in a single launch)."""
+    import torch
+    from hallthrusterpem_b200.models import plume_cathode
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    n = 150_001
+    b = spt100_batch(n, 17)
+    dev = plume_cathode({k: torch.as_tensor(v, device='cuda:0') for k, v in b.items()}, 1.0, n_angles=n_angles, extras=True)
+    monkeypatch.setenv('HPEM_HOST_BATCH_BYTES', str(40_000_003))
+    monkeypatch.setenv('HPEM_HOST_CHUNK_BYTES', str(1 << 20))
+    pinned = {k: torch.as_tensor(v).pin_memory().numpy() for k, v in b.items()}
+    for inputs in (b, pinned):
+        out = plume_cathode(inputs, 1.0, n_angles=n_angles, extras=True)
+        for key in ('j_ion', 'V_cc', 'div_angle', 'T_c', 'cos_div', 'invalid'):
+            assert np.array_equal(out[key], dev[key].cpu().numpy(), equal_nan=True), key
