@@ -467,3 +467,32 @@ def test_host_pipeline_many_batches_and_chunks(n_angles, cuda_device, monkeypatc
         out = plume_cathode(inputs, 1.0, n_angles=n_angles, extras=True)
         for key in ('j_ion', 'V_cc', 'div_angle', 'T_c', 'cos_div', 'invalid'):
             assert np.array_equal(out[key], dev[key].cpu().numpy(), equal_nan=True), key
+
+
+@pytest.mark.parametrize('n_angles', [91, 200])
+def test_device_call_is_cuda_graph_capturable(n_angles, cuda_device):
+    """hpem_eval issues nothing but kernel launches on the caller's stream (tensor maps travel as kernel parameters), so a
+    PreparedCall can be captured into a CUDA graph and replayed on new input contents -- the launch-bound small-batch loop."""
+    import torch
+    from hallthrusterpem_b200.engine import PreparedCall
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    n = 2048
+    d = {k: torch.as_tensor(v, device='cuda:0') for k, v in spt100_batch(n, 1).items()}
+    call = PreparedCall(d, want_cathode=True, want_plume=True, sweep_radius=1.0, n_angles=n_angles, extras=True)
+    call.run()                                   # warm-up outside the capture (module load, shared-memory opt-in)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        call.run()
+    for seed in (2, 3):
+        fresh = spt100_batch(n, seed)
+        for k, t in d.items():
+            t.copy_(torch.as_tensor(fresh[k]))   # same buffers, new contents
+        graph.replay()
+        torch.cuda.synchronize()
+        replayed = {k: v.clone() for k, v in call.result.items()}
+        call.run()
+        torch.cuda.synchronize()
+        for k, v in call.result.items():
+            assert torch.equal(replayed[k], v) or torch.equal(torch.isnan(replayed[k]), torch.isnan(v)), k
+        assert torch.isfinite(replayed['j_ion']).all()
