@@ -281,7 +281,7 @@ int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store
         // mode (32 x A tile <= 16 KB), larger odd A through the four-lane sweep with whole-row bulk stores (K1v)
         const bool tma16_ok = store_j && (A % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.j_ion) & 15u) == 0) && !(flags & HPEM_FLAG_NO_TMA);
         const bool lanes1 = (flags & HPEM_FLAG_LANES1) ? true : (flags & HPEM_FLAG_LANES4) ? false
-                                                                 : (A % 2 == 0 || rows_fit || quad_ok);
+                                                                 : (!store_j || A % 2 == 0 || rows_fit || quad_ok);
         // one staging buffer per warp (twice the resident warps) while the per-sample prologue dominates: measured cross-over
         // at ~160 angles for the (n, A) boxes and ~200 for the quad-row mode (tools/variant_angles.py)
         const bool one_buf = A <= (quad_ok ? kOneBufferMaxAnglesQuad : kOneBufferMaxAngles);
