@@ -105,3 +105,43 @@ def test_compression_full_size_properties(cuda_device):
     assert rel <= 2 * 0.01, rel                      # generalisation of the 1% tolerance from 500 to 1e6 samples
     j_hat = c.reconstruct_field(z)
     assert torch.allclose(torch.log10(j_hat), x_hat, rtol=0, atol=1e-12)
+
+
+def test_compression_c_abi_error_reporting(cuda_device):
+    """Misuse of the compression entry points returns a negative status with a message (never a crash, never an exception
+    across the C ABI); the Python layer raises."""
+    import ctypes
+    import torch
+    from hallthrusterpem_b200 import _lib
+    from hallthrusterpem_b200.compression import SVD
+    from hallthrusterpem_b200.engine import get_grid
+    lib = _lib.load()
+    dptr = ctypes.POINTER(ctypes.c_double)
+    proj = np.eye(8, 3)
+    h = ctypes.c_void_p()
+    assert lib.hpem_basis_create(0, 8, 0, proj.ctypes.data_as(dptr), 1, ctypes.byref(h)) == -1          # rank out of range
+    assert b'rank' in lib.hpem_last_error()
+    assert lib.hpem_basis_create(0, 8, 33, proj.ctypes.data_as(dptr), 1, ctypes.byref(h)) == -1
+    assert lib.hpem_basis_create(99, 8, 3, proj.ctypes.data_as(dptr), 1, ctypes.byref(h)) == -1         # no such device
+    assert lib.hpem_basis_create(0, 8, 3, None, 1, ctypes.byref(h)) == -1
+    assert lib.hpem_basis_create(0, 8, 3, proj.ctypes.data_as(dptr), 1, ctypes.byref(h)) == 0
+    grid = get_grid(0, 91, np.array([1.0]))
+    z = torch.empty(4, 3, dtype=torch.float64, device='cuda:0')
+    ins = _lib.HpemInputs()
+    rc = lib.hpem_compress(grid.handle, h, 4, ctypes.byref(ins), 133.322, ctypes.c_void_p(z.data_ptr()), None)
+    assert rc == -1 and b'rows' in lib.hpem_last_error()                                                 # dof 8 != 91 angles
+    assert lib.hpem_compress_field(h, -1, ctypes.c_void_p(z.data_ptr()), ctypes.c_void_p(z.data_ptr()), None) == -1
+    assert lib.hpem_reconstruct(h, 4, None, ctypes.c_void_p(z.data_ptr()), None) == -1
+    assert lib.hpem_reconstruct(h, 0, ctypes.c_void_p(z.data_ptr()), ctypes.c_void_p(z.data_ptr()), None) == 0   # empty batch is fine
+    assert lib.hpem_basis_destroy(h) == 0 and lib.hpem_basis_destroy(None) == 0
+    c = SVD(rank=2)
+    c.compute_map(np.random.default_rng(0).normal(size=(16, 40)))
+    with pytest.raises(ValueError):
+        c.compress(np.zeros((5, 15)))                                                                    # wrong dof
+    with pytest.raises(ValueError):
+        c.reconstruct(np.zeros((5, 3)))                                                                  # wrong rank
+    with pytest.raises(KeyError):
+        c.compress_inputs({'P_b': 1e-5})                                                                 # missing plume inputs
+    with pytest.raises(ValueError):
+        big = SVD(rank=40)
+        big.compute_map(np.random.default_rng(1).normal(size=(64, 100)))                                 # more than 32 coefficients
