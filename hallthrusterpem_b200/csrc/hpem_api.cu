@@ -778,7 +778,11 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
     if (smem > smem_budget)
         return fail(HPEM_ERR_UNSUPPORTED, "histogram/angle configuration needs %zu bytes of shared memory (> %zu): "
                     "raise hist_angle_stride or lower hist_sub_bits", smem, smem_budget);
-    rc = sampler ? set_smem(moments_kernel<true>, smem) : set_smem(moments_kernel<false>, smem);
+    const int hs = spec->hist_angle_stride == 0 ? 0 : (spec->hist_angle_stride == 8 ? 8 : -1);
+#define HPEM_MOMENTS_SMEM(S, H) rc = set_smem(moments_kernel<S, H>, smem)
+    if (sampler) { if (hs == 0) HPEM_MOMENTS_SMEM(true, 0); else if (hs == 8) HPEM_MOMENTS_SMEM(true, 8); else HPEM_MOMENTS_SMEM(true, -1); }
+    else         { if (hs == 0) HPEM_MOMENTS_SMEM(false, 0); else if (hs == 8) HPEM_MOMENTS_SMEM(false, 8); else HPEM_MOMENTS_SMEM(false, -1); }
+#undef HPEM_MOMENTS_SMEM
     if (rc != HPEM_OK) return rc;
     const int threads = warps * 32;
     int sm_smem = 0;
@@ -817,10 +821,10 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
     m.partial_minmax = ws.d_partial_minmax;
     SamplerParams sp_zero;
     std::memset(&sp_zero, 0, sizeof(sp_zero));
-    if (sampler)
-        moments_kernel<true><<<blocks, threads, smem, st>>>(p, m, *sampler);
-    else
-        moments_kernel<false><<<blocks, threads, smem, st>>>(p, m, sp_zero);
+#define HPEM_MOMENTS_LAUNCH(S, H, SP) moments_kernel<S, H><<<blocks, threads, smem, st>>>(p, m, SP)
+    if (sampler) { if (hs == 0) HPEM_MOMENTS_LAUNCH(true, 0, *sampler); else if (hs == 8) HPEM_MOMENTS_LAUNCH(true, 8, *sampler); else HPEM_MOMENTS_LAUNCH(true, -1, *sampler); }
+    else         { if (hs == 0) HPEM_MOMENTS_LAUNCH(false, 0, sp_zero); else if (hs == 8) HPEM_MOMENTS_LAUNCH(false, 8, sp_zero); else HPEM_MOMENTS_LAUNCH(false, -1, sp_zero); }
+#undef HPEM_MOMENTS_LAUNCH
     HPEM_CUDA(cudaGetLastError());
     const int fthreads = 256;
     moments_finalize_kernel<<<(unsigned)((lay.n_sums + fthreads - 1) / fthreads), fthreads, 0, st>>>(

@@ -1354,7 +1354,9 @@ __device__ __forceinline__ void hist_flush(unsigned* hist, const unsigned short*
     __syncwarp();
 }
 
-template <bool SAMPLED>
+// HS: histogram angle stride known at compile time (8, the default: the two histogrammed angles of a chunk are binned
+// straight from registers inside the unrolled sweep), 0 = no histograms, -1 = any stride (bins read back from the tile)
+template <bool SAMPLED, int HS>
 __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams p, const MomentsParams m,
                                                                const __grid_constant__ SamplerParams sp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -1474,6 +1476,8 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
             }
             double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec;
             double r1 = b1.rc, r2 = b2.rc;
+            constexpr int kHj = HS > 0 ? kChunk / HS : 1;
+            double hj[kHj];                              // j at the histogrammed angles of this chunk (HS > 0)
             if (plain) {
 #pragma unroll
                 for (int kk = 0; kk < kChunk; ++kk) {
@@ -1481,7 +1485,9 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
                     const double sum = e1 + e2;
                     den = fma(w.x, sum, den);
                     num = fma(w.y, sum, num);
-                    my_row[kk] = sum + j_cex;            // the value current_density() returns (columns >= A are never read back)
+                    const double jv = sum + j_cex;       // the value current_density() returns (columns >= A are never read back)
+                    my_row[kk] = jv;
+                    if (HS > 0 && kk % (HS > 0 ? HS : 1) == 0) hj[kk / (HS > 0 ? HS : 1)] = jv;
                     e1 *= r1; r1 *= b1.q;
                     e2 *= r2; r2 *= b2.q;
                 }
@@ -1492,7 +1498,9 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
                     const double sum = e1 + e2;
                     den = fma(w.x, sum, den);
                     num = fma(w.y, sum, num);
-                    my_row[kk] = invalid ? j_fill : sum + j_cex;
+                    const double jv = invalid ? j_fill : sum + j_cex;
+                    my_row[kk] = jv;
+                    if (HS > 0 && kk % (HS > 0 ? HS : 1) == 0) hj[kk / (HS > 0 ? HS : 1)] = jv;
                     e1 *= r1; r1 *= b1.q;
                     e2 *= r2; r2 *= b2.q;
                 }
@@ -1500,7 +1508,21 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
             beam_next_chunk(b1);
             beam_next_chunk(b2);
             // histogram bins of the selected angles of this chunk -> slot buffer (own row; the angle is warp-uniform)
-            if (hist_any) {
+            if (HS > 0) {
+#pragma unroll
+                for (int e = 0; e < kHj; ++e) {
+                    if (i0 + e * HS < A) {
+                        const int hi = __double2hiint(hj[e]);
+                        const int b = hi < 0 ? 0 : min(max((hi >> h_shift) - h_lo_key, 0), h_last);
+                        hbuf[lane * kHbufPitch + hslot] = row_ok ? (unsigned short)b : kHbufSkip;
+                        if (++hslot == 32) {
+                            hist_flush(hist, hbuf, lane, hslot_base, 32, hpitch);
+                            hslot_base += 32;
+                            hslot = 0;
+                        }
+                    }
+                }
+            } else if (HS < 0 && hist_any) {
                 const int i_end = min(i0 + kChunk, A);
                 for (int i = (i0 + h_stride - 1) & ~(h_stride - 1); i < i_end; i += h_stride) {
                     // log-linear bin from the leading bits of the fp64 pattern (see hist_bin)
@@ -1537,7 +1559,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
             }
             __syncwarp();
         }
-        if (hist_any && hslot > 0) hist_flush(hist, hbuf, lane, hslot_base, hslot, hpitch);
+        if (HS != 0 && hist_any && hslot > 0) hist_flush(hist, hbuf, lane, hslot_base, hslot, hpitch);
         double cd = num / den;
         if (cd == CUDART_INF) cd = CUDART_NAN;
         if (active) {
