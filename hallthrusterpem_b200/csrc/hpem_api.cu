@@ -144,6 +144,9 @@ void fill_params(const hpem_grid& g, const hpem_inputs& in, const hpem_outputs& 
     p.radius0 = g.radius0;
     p.has_thrust = out.T_c != nullptr;
     p.bulk_ok = false;
+    // rows that own their 128-byte lines may leave L2 early; rows that share lines with their neighbours should stay
+    static const int hint_env = []() { const char* v = std::getenv("HPEM_L2_HINT"); return v ? std::atoi(v) : -1; }();
+    p.l2_hint = hint_env >= 0 ? hint_env : (((long long)g.n_angles * g.n_radii) % 16 == 0 ? 2 : 1);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time dependency on libcuda)

@@ -63,6 +63,7 @@ struct EvalParams {
     // quad-row store mode (kStoreQuad): per row phase (sample index mod 4) the elements before the first / after the last
     // 32-byte-aligned body element, and the common body length (multiple of 4)
     int q_lead[4], q_tail[4], q_body;
+    int l2_hint;             // K1u tensor stores: 0 normal, 1 evict_last, 2 evict_first (see l2_store_policy)
 };
 
 struct JMaps {               // tensor maps of j_ion: [0] the (n, A) view; quad-row mode: one pair per row phase
@@ -99,6 +100,31 @@ __device__ __forceinline__ void tma_issue_2d(const CUtensorMap* map, uint32_t sm
 __device__ __forceinline__ void tma_issue_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
                  "r"(c1), "r"(c2), "r"(smem_src)
+                 : "memory");
+}
+// L2 eviction policy for the j_ion store stream (K1u).  Measured on B200: when consecutive rows share 128-byte lines (row
+// pitch not a multiple of 128 B) evict_last keeps a line in L2 until its other half arrives (A = 91: 0.181 -> 0.174 ms);
+// when every row owns its lines evict_first lets finished lines leave early (A = 256 / 512: -1 %); the wrong hint costs
+// up to 10 %.  0 = normal, 1 = evict_last, 2 = evict_first.
+__device__ __forceinline__ unsigned long long l2_store_policy(int hint) {
+    unsigned long long pol;
+    if (hint == 1)
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else if (hint == 2)
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_issue_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, unsigned long long pol) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(smem_src), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_issue_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2,
+                                             unsigned long long pol) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(smem_src), "l"(pol)
                  : "memory");
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -398,26 +424,27 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
                         __syncwarp();
                         const int c_first = c - (c % kTmaCB);
                         const bool whole = c_first + kTmaCB <= A_sweep / kChunk;
+                        const unsigned long long pol = l2_store_policy(p.l2_hint);
                         if (QUAD) {
                             // lanes 0-3 ship the four phases in parallel (one instruction sequence instead of four);
                             // bulk-group bookkeeping is per thread, so each of them commits and waits for its own ops
                             if (lane < 4) {
                                 const uint32_t src = smem_u32(group_buf + lane * (kTmaCB * 1024));
                                 if (whole) {
-                                    tma_issue_3d(&maps.m3[lane], src, 0, tma_row0, c_first);
+                                    tma_issue_3d(&maps.m3[lane], src, 0, tma_row0, c_first, pol);
                                 } else {
                                     for (int cc = c_first; cc <= c; ++cc)
-                                        tma_issue_2d(&maps.m2[lane], src + (cc - c_first) * 1024, cc * kChunk, tma_row0);
+                                        tma_issue_2d(&maps.m2[lane], src + (cc - c_first) * 1024, cc * kChunk, tma_row0, pol);
                                 }
                                 tma_commit();
                                 tma_wait_read<NBUF - 1>();   // the buffer the next group goes into is free again
                             }
                         } else if (lane == 0) {
                             if (whole) {
-                                tma_issue_3d(&maps.m3[0], smem_u32(group_buf), 0, tma_row0, c_first);
+                                tma_issue_3d(&maps.m3[0], smem_u32(group_buf), 0, tma_row0, c_first, pol);
                             } else {
                                 for (int cc = c_first; cc <= c; ++cc)
-                                    tma_issue_2d(&maps.m2[0], smem_u32(group_buf + (cc - c_first) * kTmaTileBytes), cc * kChunk, tma_row0);
+                                    tma_issue_2d(&maps.m2[0], smem_u32(group_buf + (cc - c_first) * kTmaTileBytes), cc * kChunk, tma_row0, pol);
                             }
                             tma_commit();
                             tma_wait_read<NBUF - 1>();   // the buffer the next group goes into is free again
