@@ -494,7 +494,7 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
             const double* bp = bsec + lane;
 #pragma unroll
             for (int it = 0; it < kBsecSlots; ++it) {
-                if (slot_ok && warp_s0 + 4 * it + f < p.n) __stcs(gp, bp[it * 32]);   // n % 4 == 0: row r+1 exists whenever its lead is non-empty
+                if (slot_ok && warp_s0 + 4 * it + f < p.n) *gp = bp[it * 32];         // n % 4 == 0: row r+1 exists whenever its lead is non-empty
                 gp += 4 * (long long)A;
             }
         }
