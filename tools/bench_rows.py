@@ -110,7 +110,7 @@ def main():
              'evals/s', ms, 'hbm', 8 + 144 / A, f'{8 + 144 / A:.3f} B/eval (8 + 144/A)', c)
 
     # ---- (f1) multi-radius sweep ----
-    n, A, R = 100_000, 91, 25
+    n, A, R = 400_000, 91, 25      # 7.3 GB of j_ion: several waves of blocks (1e5 samples is under two)
     b = spt100_batch(n, 8, c3_test_range=True)
     radii = np.linspace(1.0, 1.2, R)
     call = PreparedCall(dev(b), want_cathode=False, want_plume=True, sweep_radius=radii, n_angles=A)
