@@ -106,7 +106,7 @@ def main():
         small = {k: v[:20000] for k, v in b.items()}
         c = cpu(lambda: (cathode_coupling_oracle(small, TORR), current_density_oracle(small, 1.0, A, TORR)), min(n, 20000) * A,
                 'evals/s', f'{min(n, 20000)} samples x {A} angles')
-        emit(label, 'eval_uniform_kernel / eval_lanes4_kernel', f'{n} samples x {A} angles, all outputs materialised', n * A,
+        emit(label, 'eval_uniform_kernel', f'{n} samples x {A} angles, all outputs materialised', n * A,
              'evals/s', ms, 'hbm', 8 + 144 / A, f'{8 + 144 / A:.3f} B/eval (8 + 144/A)', c)
 
     # ---- (f1) multi-radius sweep ----
@@ -118,7 +118,7 @@ def main():
     small = {k: v[:2000] for k, v in b.items()}
     c = cpu(lambda: current_density_oracle(small, radii, A, TORR), 2000 * A * R, 'sample x angle x radius /s', f'2000 samples x {A} x {R}')
     per = 8 + (144 + 16 * R) / (A * R)
-    emit('f1', 'eval_multi_radius_kernel', f'{n} samples x {A} angles x {R} radii (tests/test_plume.py:31-35 shape)', n * A * R,
+    emit('f1', 'eval_radii_stream_kernel', f'{n} samples x {A} angles x {R} radii (tests/test_plume.py:31-35 shape)', n * A * R,
          'sample x angle x radius /s', ms, 'hbm', per, f'{per:.3f} B per (sample, angle, radius)', c)
 
     # ---- (f2) interpolation to probe angles + Gaussian log-likelihood ----
