@@ -12,7 +12,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .engine import _Batch, get_grid, torr_2_pa
+from .engine import _Batch, _is_torch_tensor as _is_torch, get_grid, torr_2_pa
 
 
 class JionMeasurements:
@@ -49,12 +49,19 @@ class JionMeasurements:
 
 def jion_log_likelihood(inputs: dict, meas: JionMeasurements, *, torr: float | None = None, return_pred: bool = False):
     """Gaussian log-likelihood of the probe data under the plume model for every sample of `inputs`
-    (torch CUDA float64 tensors / scalars with the plume input names).  Returns a torch tensor of loop shape
-    (and the interpolated predictions, loop shape + (m,), with `return_pred`)."""
+    (torch CUDA float64 tensors -> torch results on the device; NumPy arrays / scalars -> NumPy results).  Returns the
+    log-likelihood of loop shape (and the interpolated predictions, loop shape + (m,), with `return_pred`)."""
     import torch
     batch = _Batch(inputs, _lib.PLUME_INPUTS)
-    if not batch.on_device or batch.device_index != meas.device:
-        raise ValueError('jion_log_likelihood expects torch CUDA inputs on the device of the measurement set')
+    if not batch.on_device:        # NumPy / scalar inputs (an MCMC step): through the device, NumPy back
+        moved = {k: (torch.as_tensor(np.asarray(inputs[k], dtype=np.float64), device=f'cuda:{meas.device}')
+                     if np.ndim(inputs[k]) > 0 else inputs[k]) for k in _lib.PLUME_INPUTS}
+        if not any(_is_torch(v) for v in moved.values()):      # all scalars: one sample
+            moved['P_b'] = torch.as_tensor(np.atleast_1d(np.float64(inputs['P_b'])), device=f'cuda:{meas.device}')
+        res = jion_log_likelihood(moved, meas, torr=torr, return_pred=return_pred)
+        return tuple(r.cpu().numpy() for r in res) if return_pred else res.cpu().numpy()
+    if batch.device_index != meas.device:
+        raise ValueError('jion_log_likelihood expects inputs on the device of the measurement set')
     dev = f'cuda:{meas.device}'
     ll = torch.empty(batch.out_shape, dtype=torch.float64, device=dev)
     pred = torch.empty(batch.out_shape + (meas.m,), dtype=torch.float64, device=dev) if return_pred else None

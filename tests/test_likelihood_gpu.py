@@ -50,3 +50,18 @@ def test_loglike_rejects_out_of_range_angles(cuda_device):
     from hallthrusterpem_b200.likelihood import JionMeasurements
     with pytest.raises(ValueError):
         JionMeasurements([0.1, 1.6], [1.0, 1.0], [0.1, 0.1], n_angles=91, device=0)
+
+
+def test_loglike_accepts_host_inputs(cuda_device):
+    """NumPy arrays and plain scalars (one MCMC step) go through the same kernel and come back as NumPy."""
+    import torch
+    from hallthrusterpem_b200.likelihood import JionMeasurements, jion_log_likelihood
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    b = {k: v for k, v in spt100_batch(257, 3).items() if k in ('P_b', 'c0', 'c1', 'c2', 'c3', 'c4', 'c5', 'sigma_cex', 'I_B0')}
+    meas = JionMeasurements(np.linspace(-1.2, 1.2, 9), np.full(9, 0.5), np.full(9, 0.1), n_angles=91, device=0)
+    dev = jion_log_likelihood({k: torch.as_tensor(v, device='cuda:0') for k, v in b.items()}, meas, torr=133.322)
+    host, pred = jion_log_likelihood(b, meas, torr=133.322, return_pred=True)
+    assert isinstance(host, np.ndarray) and host.shape == (257,) and pred.shape == (257, 9)
+    assert np.array_equal(host, dev.cpu().numpy())
+    one = jion_log_likelihood({k: float(v[5]) for k, v in b.items()}, meas, torr=133.322)
+    assert one.shape == (1,) and one[0] == host[5]
