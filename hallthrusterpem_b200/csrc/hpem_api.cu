@@ -229,7 +229,10 @@ int launch(const hpem_grid& g, const hpem::EvalParams& p, bool plume, bool store
     const bool use_multi = plume && store_j && g.uniform && g.n_radii > 1 && g.n_radii <= kMaxRadiiFast && g.smem_ok &&
                            !(flags & HPEM_FLAG_FORCE_DIRECT);
     const size_t smem_w = k1w_smem_bytes(g.n_angles, g.n_angles_pad, g.n_radii);
-    const bool use_stream = plume && g.n_radii >= kMinRadiiStream && smem_w <= 100 * 1024 && (long long)g.n_angles * g.n_radii < (1LL << 25) &&
+    // K1w for many radii, and for a few radii whenever the row length A*R is odd (K1r has no tensor map there and falls back
+    // to plain stores: 0.104 vs 0.151 ms at 91 angles x 7 radii); K1r keeps the short even rows (A = 200, R = 3: 0.098 vs 0.130 ms)
+    const bool odd_rows = ((long long)g.n_angles * g.n_radii) % 2 == 1;
+    const bool use_stream = plume && g.n_radii >= 2 && (g.n_radii >= kMinRadiiStream || odd_rows) && smem_w <= 100 * 1024 && (long long)g.n_angles * g.n_radii < (1LL << 25) &&
                             !(flags & (HPEM_FLAG_FORCE_DIRECT | HPEM_FLAG_LANES1));
     if (use_stream) {   // K1w: many radii -- per-sample tables + one contiguous store stream per 8 samples (any grid)
         const unsigned blocks = (unsigned)((p.n + kThreadsW - 1) / kThreadsW);
