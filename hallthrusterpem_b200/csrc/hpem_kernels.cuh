@@ -74,8 +74,10 @@ struct JMaps {               // tensor maps of j_ion: [0] the (n, A) view; quad-
 constexpr int kChunk = 16;          // angles per staged tile / inner recurrence length
 constexpr int kRestartChunks = 16;  // exact exp() restart every kRestartChunks*kChunk angles
 constexpr int kTilePitch = kChunk + 1;
-// 64-thread blocks: blocks retire and start at a finer grain, which keeps warps of one SM in different phases
-// (per-sample prologue vs store-bound sweep); measured 0.309 ms vs 0.336 ms with 128 threads (1e6 x 200, B200)
+// Small blocks: blocks retire and start at a fine grain, which keeps the warps of one SM in different phases (per-sample
+// prologue vs store-bound sweep); 1e6 x 200 on B200: 0.336 ms with 128 threads, 0.311 with 64, 0.306 with 32.  One-warp
+// blocks win only for K1u's (n, A) tensor-store mode with two staging buffers (long aligned rows); everything else
+// (quad-row mode, single-buffer mode for short rows) is 2-6 % faster with two warps per block.
 #ifndef HPEM_THREADS_U
 #define HPEM_THREADS_U 64
 #endif
@@ -217,7 +219,7 @@ __device__ __forceinline__ void beam_next_chunk(BeamState& b) {
 }
 
 #ifndef HPEM_MIN_BLOCKS_U
-#define HPEM_MIN_BLOCKS_U 6
+#define HPEM_MIN_BLOCKS_U (384 / HPEM_THREADS_U)      // 12 resident warps per SM with two staging buffers per warp
 #endif
 // j_ion staging / store modes of K1u
 constexpr int kStoreStg = 0;    // 32x16 tile, transposed read-back, plain streaming stores (any A, any alignment)
@@ -240,12 +242,14 @@ constexpr int kBsecBytes = 32 * kBsecSlots * 8;     // per warp
 // NBUF staging buffers per warp: 2 overlap the fill of one group with the TMA read of the other (best for long rows);
 // 1 halves shared memory and almost doubles the resident warps, which wins while the per-sample prologue dominates
 // (A <~ 128: 0.120 ms vs 0.148 ms at 1e6 x 64, B200)
-template <bool WANT_PLUME, bool STORE_J, int MODE, int NBUF>
-__global__ void __launch_bounds__(kThreadsU, NBUF == 1 ? 10 : HPEM_MIN_BLOCKS_U)
+template <bool WANT_PLUME, bool STORE_J, int MODE, int NBUF, int THREADS = kThreadsU>
+__global__ void __launch_bounds__(THREADS, (NBUF == 1 ? 640 : 384) / THREADS)   // 20 resident warps with one staging buffer, 12 with two
 eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // layout: [staging tiles (1024-byte aligned for the 128B TMA swizzle)] [row-boundary buffers (quad mode)] [fused weights]
     unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int kThreadsU = THREADS;           // shadow the file-level defaults: this kernel is instantiated per block size
+    constexpr int kWarpsU = THREADS / 32;
     constexpr bool QUAD = (MODE == kStoreQuad);
     constexpr bool USE_TMA = (MODE == kStoreTma) || QUAD;
     constexpr bool ROWS = (MODE == kStoreRows);
@@ -555,7 +559,7 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
 constexpr int kMaxRadiiFast = 48;   // 2 * R * 128 * 8 B of shared memory per block
 
 template <bool USE_TMA>
-__global__ void __launch_bounds__(kThreadsU, 3) eval_multi_radius_kernel(const EvalParams p,
+__global__ void __launch_bounds__(kThreadsU, 192 / kThreadsU) eval_multi_radius_kernel(const EvalParams p,
                                                                          const __grid_constant__ CUtensorMap jmap) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
