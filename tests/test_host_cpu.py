@@ -292,3 +292,24 @@ def test_pinned_output_pool_reuses_buffers(monkeypatch):
     assert len(allocations) <= 4
     m = pool.take((7, 3), np.uint8)
     assert m.shape == (7, 3) and m.dtype == np.uint8
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle timed on the host cores) runs without a GPU and prints ONE JSON line with the
+    keys the driver reads; under torchrun only rank 0 prints."""
+    import json
+    import os
+    import subprocess
+    import sys
+    cmd = [sys.executable, str(ROOT / 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0']
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK='0', WORLD_SIZE='1'))
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'evals/s' and d['higher_is_better'] is True and d['value'] > 1e6
+    assert d['metric'] == 'plume+cathode fp64 sample x angle evals/s' and d['config']['n_angles'] == 200
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK='1', WORLD_SIZE='2'))
+    assert res.returncode == 0 and not [ln for ln in res.stdout.splitlines() if ln.startswith('{')]
