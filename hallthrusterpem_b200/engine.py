@@ -254,6 +254,11 @@ class PreparedCall:
             names += tuple(k for k in _lib.PLUME_INPUTS if k not in names)
         self.batch = batch = _Batch(inputs, names, optional=('T',) if want_plume else ())
         has_thrust = 'T' in batch.present
+        if want_plume and batch.n == 0:
+            # the reference fails on an empty sample batch, too: scipy.integrate.simpson (plume.py:122) cannot broadcast
+            # its slices of a (0, A, R) integrand.  cathode_coupling alone returns an empty V_cc, here as there.
+            raise ValueError('operands could not be broadcast together: current_density needs at least one sample '
+                             '(the reference raises the same from scipy.integrate.simpson, plume.py:122)')
         self.torr = torr_2_pa() if torr is None else float(torr)
         self.want_plume = want_plume
 

@@ -313,3 +313,15 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d['e2e'] == {'value': d['value'], 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK='1', WORLD_SIZE='2'))
     assert res.returncode == 0 and not [ln for ln in res.stdout.splitlines() if ln.startswith('{')]
+
+
+def test_empty_batch_raises_like_the_reference():
+    """plume.py:122: scipy's simpson cannot handle a (0, A, R) integrand, so the reference raises ValueError for an empty
+    sample batch; the drop-in raises the same error class (before touching the GPU)."""
+    from hallthrusterpem_b200.models import current_density
+    from oracle.ref_restated import current_density_oracle
+    empty = {k: np.zeros(0) for k in ('P_b', 'c0', 'c1', 'c2', 'c3', 'c4', 'c5', 'sigma_cex', 'I_B0')}
+    with pytest.raises(ValueError):
+        current_density_oracle(empty, 1.0, 91)
+    with pytest.raises(ValueError):
+        current_density(empty)

@@ -496,3 +496,17 @@ def test_device_call_is_cuda_graph_capturable(n_angles, cuda_device):
         for k, v in call.result.items():
             assert torch.equal(replayed[k], v) or torch.equal(torch.isnan(replayed[k]), torch.isnan(v)), k
         assert torch.isfinite(replayed['j_ion']).all()
+
+
+def test_empty_batches(cuda_device):
+    """cathode_coupling on an empty batch returns an empty V_cc (as the reference does); current_density raises ValueError
+    (as the reference does, from scipy's simpson)."""
+    import torch
+    cathode_coupling, current_density, _ = _models()
+    names = ('P_b', 'V_a', 'T_e', 'V_vac', 'Pstar', 'P_T')
+    v = cathode_coupling({k: np.zeros(0) for k in names})['V_cc']
+    assert isinstance(v, np.ndarray) and v.shape == (0,) and v.dtype == np.float64
+    vd = cathode_coupling({k: torch.zeros(0, dtype=torch.float64, device='cuda:0') for k in names})['V_cc']
+    assert vd.is_cuda and tuple(vd.shape) == (0,)
+    with pytest.raises(ValueError):
+        current_density({k: np.zeros(0) for k in ('P_b', 'c0', 'c1', 'c2', 'c3', 'c4', 'c5', 'sigma_cex', 'I_B0')})
