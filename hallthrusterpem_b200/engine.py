@@ -312,6 +312,8 @@ class PreparedCall:
         """Device inputs: asynchronous launch on `stream` (default: torch's current stream).
         Host inputs: returns when every output has landed in host memory."""
         b = self.batch
+        if b.n == 0:          # empty batch (cathode only): nothing to launch, and empty buffers have no address to pass
+            return
         if b.on_device:
             torch = _torch()
             if stream is None:
