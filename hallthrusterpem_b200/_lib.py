@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = (
     'hpem_abi_version', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',
     'hpem_eval', 'hpem_eval_host', 'hpem_launch_count',
     'hpem_moments_layout_query', 'hpem_moments_accumulate', 'hpem_sample_inputs', 'hpem_moments_accumulate_sampled',
-    'hpem_measurements_create', 'hpem_measurements_destroy', 'hpem_loglike',
+    'hpem_measurements_create', 'hpem_measurements_destroy', 'hpem_loglike', 'hpem_logsumexp',
     'hpem_basis_create', 'hpem_basis_destroy', 'hpem_compress', 'hpem_compress_field', 'hpem_reconstruct',
 )
 
@@ -161,6 +161,8 @@ def load() -> ctypes.CDLL:
         lib.hpem_measurements_destroy.restype = i32
         lib.hpem_loglike.argtypes = [vp, vp, i64, ctypes.POINTER(HpemInputs), dbl, vp, vp, vp]
         lib.hpem_loglike.restype = i32
+        lib.hpem_logsumexp.argtypes = [i32, i64, i32, vp, vp, vp]
+        lib.hpem_logsumexp.restype = i32
         lib.hpem_basis_create.argtypes = [i32, i32, i32, dptr, i32, ctypes.POINTER(vp)]
         lib.hpem_basis_create.restype = i32
         lib.hpem_basis_destroy.argtypes = [vp]

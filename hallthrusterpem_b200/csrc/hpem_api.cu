@@ -979,6 +979,20 @@ int hpem_measurements_destroy(hpem_measurements* h) {
     return HPEM_OK;
 }
 
+int hpem_logsumexp(int device, int64_t n_groups, int m, const double* loglike, double* out, void* stream) {
+    if (!loglike || !out) return fail(HPEM_ERR_INVALID_ARG, "NULL argument");
+    if (n_groups < 0 || m < 1) return fail(HPEM_ERR_INVALID_ARG, "need n_groups >= 0 and m >= 1");
+    if (n_groups == 0) return HPEM_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", device);
+    const int64_t blocks = (n_groups + 3) / 4;
+    if (blocks > 2147483647LL) return fail(HPEM_ERR_INVALID_ARG, "too many groups for one call");
+    hpem::logsumexp_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(loglike, n_groups, m, out);
+    HPEM_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return HPEM_OK;
+}
+
 int hpem_loglike(const hpem_grid* g, const hpem_measurements* meas, int64_t n, const hpem_inputs* in, double torr_2_pa,
                  double* loglike, double* y_pred, void* stream) {
     if (!g || !meas || !in) return fail(HPEM_ERR_INVALID_ARG, "NULL argument");

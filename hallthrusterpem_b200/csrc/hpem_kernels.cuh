@@ -1782,4 +1782,28 @@ __global__ void __launch_bounds__(kThreadsL) loglike_kernel(const EvalParams p, 
     if (lp.loglike) lp.loglike[s] = ll;
 }
 
+// log-sum-exp over the trailing axis (the M Monte-Carlo draws of the nuisance parameters behind one calibration vector):
+// out[g] = max_m ll[g, m] + log(sum_m exp(ll[g, m] - max))   -- scripts/pem_v0/mcmc.py:101-102.  One warp per group.
+__global__ void __launch_bounds__(128) logsumexp_kernel(const double* __restrict__ ll, long long n_groups, int m,
+                                                        double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long g = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (g >= n_groups) return;
+    const double* row = ll + g * (long long)m;
+    double mx = -CUDART_INF;
+    bool any_nan = false;
+    for (int i = lane; i < m; i += 32) {
+        const double v = __ldg(row + i);
+        any_nan |= (v != v);
+        mx = fmax(mx, v);                       // fmax skips NaN; np.max propagates it -> handled below
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    any_nan = __any_sync(0xffffffffu, any_nan);
+    double sum = 0.0;
+    for (int i = lane; i < m; i += 32) sum += exp(__ldg(row + i) - mx);
+    sum = warp_sum(sum);
+    if (lane == 0) out[g] = any_nan ? CUDART_NAN : mx + log(sum);   // all -inf: -inf + log(nan) = nan, as in NumPy
+}
+
 }  // namespace hpem

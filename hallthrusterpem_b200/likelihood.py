@@ -70,3 +70,25 @@ def jion_log_likelihood(inputs: dict, meas: JionMeasurements, *, torr: float | N
                                      torr_2_pa() if torr is None else float(torr), ctypes.c_void_p(ll.data_ptr()),
                                      ctypes.c_void_p(pred.data_ptr()) if return_pred else None, ctypes.c_void_p(stream)))
     return (ll, pred) if return_pred else ll
+
+
+def marginal_log_likelihood(loglike):
+    """Log-sum-exp of per-draw log-likelihoods over the trailing axis (the M Monte-Carlo draws of the nuisance parameters
+    behind one calibration vector): `max + log(sum(exp(ll - max)))`, scripts/pem_v0/mcmc.py:101-102.  torch CUDA tensor
+    `(..., M)` -> `(...,)` on the device; NumPy in -> NumPy out (through the device)."""
+    import torch
+    was_torch = _is_torch(loglike)
+    t = loglike if was_torch else torch.as_tensor(np.asarray(loglike, dtype=np.float64))
+    if not t.is_cuda:
+        if not torch.cuda.is_available():
+            raise RuntimeError('hallthrusterpem_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        t = t.cuda()
+    t = t.to(torch.float64).contiguous()
+    if t.dim() < 1 or t.shape[-1] < 1:
+        raise ValueError('need a trailing axis of at least one draw')
+    out = torch.empty(t.shape[:-1], dtype=torch.float64, device=t.device)
+    n_groups = int(np.prod(t.shape[:-1], dtype=np.int64)) if t.dim() > 1 else 1
+    dev = t.device.index
+    _lib.check(_lib.load().hpem_logsumexp(dev, n_groups, int(t.shape[-1]), ctypes.c_void_p(t.data_ptr()),
+                                          ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out if was_torch else out.cpu().numpy()

@@ -199,6 +199,11 @@ int hpem_measurements_destroy(hpem_measurements *meas);
 int hpem_loglike(const hpem_grid *grid, const hpem_measurements *meas, int64_t n, const hpem_inputs *in,
                  double torr_2_pa, double *loglike, double *y_pred, void *stream);
 
+/* Marginal log-likelihood over the trailing axis of m Monte-Carlo draws per calibration vector:
+ * out[g] = max_m ll[g, m] + log(sum_m exp(ll[g, m] - max))  (scripts/pem_v0/mcmc.py:101-102).  DEVICE buffers:
+ * loglike (n_groups, m), out (n_groups). */
+int hpem_logsumexp(int device, int64_t n_groups, int m, const double *loglike, double *out, void *stream);
+
 /* ---- SVD compression of the j_ion field quantity (the data format downstream of the path: amisc normalises j_ion
  * with log10 and keeps only its projection on the leading left-singular vectors of a compression sample set,
  * scripts/pem_v0/pem_v0_SPT-100.yml:272-280, scripts/gen_data.py:279-290; amisc itself is un-vendored, uv.lock:14-16).

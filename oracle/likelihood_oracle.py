@@ -26,3 +26,10 @@ def jion_log_likelihood_oracle(inputs: dict, theta, y, sigma, n_angles: int, tor
     pred = jion_interp_oracle(j, np.asarray(theta, dtype=np.float64), n_angles)
     ll = np.sum(-0.5 * ((np.asarray(y) - pred) / np.asarray(sigma)) ** 2, axis=-1)       # mcmc.py:103
     return ll, pred
+
+
+def marginal_log_likelihood_oracle(loglike: np.ndarray) -> np.ndarray:
+    """scripts/pem_v0/mcmc.py:101-102: log-sum-exp over the M axis."""
+    with np.errstate(all='ignore'):
+        mx = np.max(loglike, axis=-1, keepdims=True)                                           # :101
+        return np.squeeze(mx, axis=-1) + np.log(np.sum(np.exp(loglike - mx), axis=-1))        # :102

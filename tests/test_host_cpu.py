@@ -89,7 +89,7 @@ def test_c_abi_library_exports_declared_symbols():
     assert {'hpem_abi_version', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',
             'hpem_eval', 'hpem_eval_host', 'hpem_launch_count', 'hpem_moments_layout_query',
             'hpem_moments_accumulate', 'hpem_sample_inputs', 'hpem_moments_accumulate_sampled',
-            'hpem_measurements_create', 'hpem_measurements_destroy', 'hpem_loglike',
+            'hpem_measurements_create', 'hpem_measurements_destroy', 'hpem_loglike', 'hpem_logsumexp',
             'hpem_basis_create', 'hpem_basis_destroy', 'hpem_compress', 'hpem_compress_field', 'hpem_reconstruct'} == declared
     assert set(_lib.EXPORTED_SYMBOLS) == declared
     lib = ctypes.CDLL(str(path))

@@ -65,3 +65,22 @@ def test_loglike_accepts_host_inputs(cuda_device):
     assert np.array_equal(host, dev.cpu().numpy())
     one = jion_log_likelihood({k: float(v[5]) for k, v in b.items()}, meas, torr=133.322)
     assert one.shape == (1,) and one[0] == host[5]
+
+
+def test_marginal_log_likelihood_matches_oracle(cuda_device):
+    """log-sum-exp over the M draws (mcmc.py:101-102): wide dynamic range, -inf entries, NaN propagation, M = 1."""
+    import torch
+    from hallthrusterpem_b200.likelihood import marginal_log_likelihood
+    from oracle.likelihood_oracle import marginal_log_likelihood_oracle
+    rng = np.random.default_rng(4)
+    for shape in ((1000, 64), (7, 3, 33), (5, 1), (2000, 500)):
+        ll = -10.0 ** rng.uniform(-1, 4, shape)
+        ll.reshape(-1)[::97] = -np.inf
+        ll.reshape(-1, shape[-1])[3, :] = -np.inf            # a whole group at -inf: nan, as in NumPy
+        ll.reshape(-1, shape[-1])[4, 0] = np.nan
+        ref = marginal_log_likelihood_oracle(ll)
+        got = marginal_log_likelihood(torch.as_tensor(ll, device='cuda:0')).cpu().numpy()
+        assert got.shape == ref.shape and np.array_equal(np.isnan(got), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        assert np.all(np.abs(got[ok] - ref[ok]) <= 1e-12 * np.abs(ref[ok]) + 1e-13)
+        assert np.array_equal(marginal_log_likelihood(ll), got, equal_nan=True)     # NumPy in -> NumPy out
