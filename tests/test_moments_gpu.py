@@ -2,8 +2,6 @@
 import numpy as np
 import pytest
 
-from tests import parity
-
 pytestmark = pytest.mark.gpu
 
 
