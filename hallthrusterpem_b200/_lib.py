@@ -26,16 +26,19 @@ CATHODE_INPUTS = INPUT_NAMES[:6]
 PLUME_INPUTS = ('P_b',) + INPUT_NAMES[6:14]
 
 HPEM_OK = 0
+ABI_VERSION = 2
 FLAG_FORCE_DIRECT = 1
 FLAG_NO_TMA = 2
 FLAG_LANES1 = 4
 FLAG_LANES4 = 8
 FLAG_NO_QUAD = 16
+FLAG_NO_FASTMATH = 32
 
 EXPORTED_SYMBOLS = (
-    'hpem_abi_version', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',
+    'hpem_abi_version', 'hpem_source_hash', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',
     'hpem_eval', 'hpem_eval_host', 'hpem_launch_count',
     'hpem_moments_layout_query', 'hpem_moments_accumulate', 'hpem_sample_inputs', 'hpem_moments_accumulate_sampled',
+    'hpem_moments_merge',
     'hpem_measurements_create', 'hpem_measurements_destroy', 'hpem_loglike', 'hpem_logsumexp',
     'hpem_basis_create', 'hpem_basis_destroy', 'hpem_compress', 'hpem_compress_field', 'hpem_reconstruct',
 )
@@ -53,7 +56,7 @@ class HpemOutputs(ctypes.Structure):
 class HpemMomentsSpec(ctypes.Structure):
     _fields_ = [('hist_angle_stride', ctypes.c_int32), ('hist_sub_bits', ctypes.c_int32),
                 ('hist_min_exp2', ctypes.c_int32), ('hist_max_exp2', ctypes.c_int32),
-                ('want_cathode', ctypes.c_int32), ('want_thrust', ctypes.c_int32)]
+                ('want_cathode', ctypes.c_int32), ('want_thrust', ctypes.c_int32), ('scalar_shift', ctypes.c_double * 3)]
 
 
 class HpemMomentsLayout(ctypes.Structure):
@@ -77,32 +80,66 @@ class LibraryMissing(ImportError):
     pass
 
 
+HASH_MARKER = b'HPEM_SOURCE_HASH='
+
+
+def _sources() -> list[Path]:
+    return sorted(list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) + list(CSRC.glob('*.inc')) + [HEADER])
+
+
+def source_hash() -> str:
+    """SHA-256 (first 16 hex digits) over the CUDA sources and the C header -- compiled into the library
+    (`hpem_source_hash()`), so a binary that does not belong to this tree is detected whatever its mtime says."""
+    import hashlib
+    h = hashlib.sha256()
+    for p in _sources():
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def embedded_hash(path: Path) -> str | None:
+    """The source hash compiled into a built library, read from the file (no dlopen); None if absent."""
+    try:
+        data = Path(path).read_bytes()
+    except OSError:
+        return None
+    i = data.find(HASH_MARKER)
+    if i < 0:
+        return None
+    return data[i + len(HASH_MARKER): i + len(HASH_MARKER) + 16].decode('ascii', 'replace')
+
+
 def nvcc_command(out: Path = LIB_PATH) -> list[str]:
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     return [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-            '-Xcompiler', '-fPIC', '-shared', '-o', str(out), str(CSRC / 'hpem_api.cu')]
+            f'-DHPEM_SOURCE_HASH={source_hash()}', '-Xcompiler', '-fPIC', '-shared', '-o', str(out), str(CSRC / 'hpem_api.cu')]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
-    """Compile csrc/*.cu into lib/libhpem.so for sm_100a (cross-compiles without a GPU).  Safe to call from several
-    processes at once (each builds to a private temporary file and renames it into place)."""
-    sources = list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) + list(CSRC.glob('*.inc')) + [HEADER]
-    if LIB_PATH.exists() and not force:
-        newest = max(p.stat().st_mtime for p in sources)
-        if LIB_PATH.stat().st_mtime >= newest:
-            return LIB_PATH
+    """Compile csrc/*.cu into lib/libhpem.so for sm_100a (cross-compiles without a GPU) unless the library on disk already
+    carries the hash of the current sources.  Concurrent callers (the ranks of a multi-GPU launch) serialise on a lock file:
+    one compiles, the others find the fresh library when they get the lock."""
+    import fcntl
+    want = source_hash()
+    if LIB_PATH.exists() and not force and embedded_hash(LIB_PATH) == want:
+        return LIB_PATH
     LIB_PATH.parent.mkdir(parents=True, exist_ok=True)
-    tmp = LIB_PATH.with_name(f'{LIB_PATH.name}.tmp.{os.getpid()}')
-    cmd = nvcc_command(tmp)
-    if verbose:
-        cmd.insert(1, '-Xptxas=-v')
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        tmp.unlink(missing_ok=True)
-        raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)
-    os.replace(tmp, LIB_PATH)
-    if verbose:
-        print(res.stderr)
+    with open(LIB_PATH.with_name('.build.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if LIB_PATH.exists() and not force and embedded_hash(LIB_PATH) == want:
+            return LIB_PATH
+        tmp = LIB_PATH.with_name(f'{LIB_PATH.name}.tmp.{os.getpid()}')
+        cmd = nvcc_command(tmp)
+        if verbose:
+            cmd.insert(1, '-Xptxas=-v')
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            tmp.unlink(missing_ok=True)
+            raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)
+        os.replace(tmp, LIB_PATH)
+        if verbose:
+            print(res.stderr)
     return LIB_PATH
 
 
@@ -119,11 +156,17 @@ def load() -> ctypes.CDLL:
         if _lib is not None:
             return _lib
         path = Path(os.environ.get('HPEM_LIBRARY', LIB_PATH))
-        if 'HPEM_LIBRARY' not in os.environ and (shutil.which('nvcc') or Path('/usr/local/cuda/bin/nvcc').exists()):
-            try:                      # (re)build when missing or older than its sources -- this IS the product, not a fallback
-                build_library()
-            except Exception as exc:  # noqa: BLE001
-                if not path.exists():
+        if 'HPEM_LIBRARY' not in os.environ:
+            # The library must be built from THIS tree's sources (hash compiled in).  Stale or missing: rebuild when nvcc is
+            # here -- this IS the product, not a fallback -- and fail loudly otherwise; a failed rebuild never falls back to
+            # the old binary.
+            if embedded_hash(path) != source_hash():
+                if not (shutil.which('nvcc') or Path('/usr/local/cuda/bin/nvcc').exists()):
+                    raise LibraryMissing(f'{path} is missing or was not built from the sources in {CSRC} and nvcc is not '
+                                         'available: build it with `python __graft_entry__.py`. No CPU fallback exists.')
+                try:
+                    build_library()
+                except Exception as exc:  # noqa: BLE001
                     raise LibraryMissing(f'building {path} failed: {exc}') from exc
         if not path.exists():
             raise LibraryMissing(f'{path} not found: build it with `python __graft_entry__.py` '
@@ -132,6 +175,7 @@ def load() -> ctypes.CDLL:
         vp, i32, i64, dbl, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_uint32
         dptr = ctypes.POINTER(ctypes.c_double)
         lib.hpem_abi_version.restype = i32
+        lib.hpem_source_hash.restype = ctypes.c_char_p
         lib.hpem_last_error.restype = ctypes.c_char_p
         lib.hpem_launch_count.restype = i64
         lib.hpem_grid_create.argtypes = [i32, i32, dptr, dptr, dptr, i32, dptr, ctypes.POINTER(vp)]
@@ -149,6 +193,8 @@ def load() -> ctypes.CDLL:
         lib.hpem_moments_accumulate.argtypes = [vp, i64, ctypes.POINTER(HpemInputs), dbl, ctypes.POINTER(HpemMomentsSpec),
                                                 vp, vp, vp]
         lib.hpem_moments_accumulate.restype = i32
+        lib.hpem_moments_merge.argtypes = [i32, ctypes.POINTER(HpemMomentsLayout), i32, vp, i64, vp, vp, vp]
+        lib.hpem_moments_merge.restype = i32
         u64 = ctypes.c_uint64
         lib.hpem_sample_inputs.argtypes = [i32, i64, u64, u64, ctypes.POINTER(HpemPrior), ctypes.POINTER(vp), vp]
         lib.hpem_sample_inputs.restype = i32
@@ -173,8 +219,10 @@ def load() -> ctypes.CDLL:
         lib.hpem_compress_field.restype = i32
         lib.hpem_reconstruct.argtypes = [vp, i64, vp, vp, vp]
         lib.hpem_reconstruct.restype = i32
-        if lib.hpem_abi_version() != 1:
-            raise HpemError(f'libhpem ABI version {lib.hpem_abi_version()} != 1')
+        if lib.hpem_abi_version() != ABI_VERSION:
+            raise HpemError(f'libhpem ABI version {lib.hpem_abi_version()} != {ABI_VERSION}: rebuild with `python __graft_entry__.py`')
+        if 'HPEM_LIBRARY' not in os.environ and lib.hpem_source_hash().decode() != source_hash():
+            raise HpemError(f'{path} reports source hash {lib.hpem_source_hash().decode()}, the tree has {source_hash()}')
         _lib = lib
     return _lib
 

@@ -16,6 +16,7 @@
 
 #include "../../include/hpem.h"
 #include "hpem_kernels.cuh"
+#include "hpem_moments.cuh"
 #include "hpem_compress.cuh"
 
 namespace {
@@ -75,6 +76,9 @@ struct Workspace {
     size_t partials_cap = 0;
     double* d_partial_minmax = nullptr;
     size_t partial_minmax_cap = 0;
+    unsigned* d_hist_partials = nullptr;   // K2 per-block histograms; all-zero between calls (the finalize kernel re-zeroes them)
+    size_t hist_partials_cap = 0;
+    cudaEvent_t moments_done = nullptr;    // end of the last reduce-only pass that used the scratch buffers above
 };
 
 }  // namespace
@@ -147,6 +151,8 @@ void fill_params(const hpem_grid& g, const hpem_inputs& in, const hpem_outputs& 
     // rows that own their 128-byte lines may leave L2 early; rows that share lines with their neighbours should stay
     static const int hint_env = []() { const char* v = std::getenv("HPEM_L2_HINT"); return v ? std::atoi(v) : -1; }();
     p.l2_hint = hint_env >= 0 ? hint_env : (((long long)g.n_angles * g.n_radii) % 16 == 0 ? 2 : 1);
+    static const int no_fast_env = []() { const char* v = std::getenv("HPEM_NO_FASTMATH"); return v ? std::atoi(v) : 0; }();
+    p.no_fastmath = no_fast_env;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time dependency on libcuda)
@@ -362,6 +368,7 @@ int launch_range(const hpem_grid& g, const hpem_inputs& in, const hpem_outputs& 
     }
     hpem::EvalParams p;
     fill_params(g, in, out, first, count, torr, p);
+    if (flags & HPEM_FLAG_NO_FASTMATH) p.no_fastmath = 1;
     return launch(g, p, plume, store_j, flags, st);
 }
 
@@ -391,6 +398,15 @@ int grow(T*& ptr, size_t& cap, size_t need) {
 extern "C" {
 
 int hpem_abi_version(void) { return HPEM_ABI_VERSION; }
+
+#ifndef HPEM_SOURCE_HASH
+#define HPEM_SOURCE_HASH unstamped
+#endif
+#define HPEM_STR2(x) #x
+#define HPEM_STR(x) HPEM_STR2(x)
+// "HPEM_SOURCE_HASH=<16 hex digits>": the loader finds the marker in the file (no dlopen) and compares it with the tree
+static const char g_source_hash[] = "HPEM_SOURCE_HASH=" HPEM_STR(HPEM_SOURCE_HASH);
+const char* hpem_source_hash(void) { return g_source_hash + 17; }
 
 const char* hpem_last_error(void) { return g_err; }
 
@@ -448,15 +464,17 @@ int hpem_grid_create(int device, int n_angles, const double* alpha, const double
     HPEM_CUDA_G(cudaMemcpy(g->d_radii, radii, n_radii * sizeof(double), cudaMemcpyHostToDevice));
 #undef HPEM_CUDA_G
 
-    const size_t wbytes = size_t(g->n_angles_pad) * sizeof(double2) + 1024;  // + slack for the 1024-byte alignment
-    g->smem_nostore = wbytes;
-    g->smem_stg = wbytes + size_t(hpem::kWarpsU) * 32 * hpem::kTilePitch * sizeof(double);
-    g->smem_tma = wbytes + size_t(hpem::kWarpsU) * 2 * hpem::kTmaGroupBytes;
-    g->smem_tma32 = wbytes + size_t(2) * hpem::kTmaGroupBytes;
-    g->smem_tma1 = wbytes + size_t(hpem::kWarpsU) * 1 * hpem::kTmaGroupBytes;
-    g->smem_quad = g->smem_tma + size_t(hpem::kWarpsU) * hpem::kBsecBytes;
-    g->smem_quad1 = g->smem_tma1 + size_t(hpem::kWarpsU) * hpem::kBsecBytes;
-    g->smem_rows = wbytes + size_t(hpem::kWarpsU) * ((size_t(32) * n_angles * 8 + 15) & ~size_t(15));
+    const size_t wbytes = size_t(g->n_angles_pad) * sizeof(double2) + 1024;  // K1r / K1v: + slack for the 1024-byte alignment
+    // K1u: weights up to the last 16-angle chunk, no alignment slack (address-based swizzle, see the kernel)
+    const size_t wb_u = size_t((n_angles + hpem::kChunk - 1) / hpem::kChunk * hpem::kChunk) * sizeof(double2) + HPEM_SMEM_SKEW;
+    g->smem_nostore = wb_u;
+    g->smem_stg = wb_u + size_t(hpem::kWarpsU) * 32 * hpem::kTilePitch * sizeof(double);
+    g->smem_tma = wb_u + size_t(hpem::kWarpsU) * 2 * hpem::kTmaGroupBytes;
+    g->smem_tma32 = wb_u + size_t(2) * hpem::kTmaGroupBytes;
+    g->smem_tma1 = wb_u + size_t(hpem::kWarpsU) * 1 * hpem::kTmaGroupBytes;
+    g->smem_quad = g->smem_tma;      // the row-boundary buffer aliases the staging area
+    g->smem_quad1 = g->smem_tma1;
+    g->smem_rows = wb_u + size_t(hpem::kWarpsU) * ((size_t(32) * n_angles * 8 + 15) & ~size_t(15));
     const size_t xbytes = size_t(hpem::kWarpsV) * 32 * hpem::kXchPitch * sizeof(double);
     g->smem_v_nostore = wbytes + xbytes;
     g->smem_v_store = wbytes + xbytes + size_t(hpem::kWarpsV) * hpem::k1v_tile_bytes(n_angles);
@@ -493,6 +511,8 @@ int hpem_grid_destroy(hpem_grid* g) {
     if (ws.d_pack_out) cudaFree(ws.d_pack_out);
     if (ws.d_partials) cudaFree(ws.d_partials);
     if (ws.d_partial_minmax) cudaFree(ws.d_partial_minmax);
+    if (ws.d_hist_partials) cudaFree(ws.d_hist_partials);
+    if (ws.moments_done) cudaEventDestroy(ws.moments_done);
     for (auto e : ws.events) cudaEventDestroy(e);
     for (auto e : ws.h2d_events) cudaEventDestroy(e);
     if (ws.s_h2d) cudaStreamDestroy(ws.s_h2d);
@@ -538,6 +558,17 @@ int hpem_eval_host(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem_ou
     if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", g->device);
     Workspace& ws = g->ws;
     std::lock_guard<std::mutex> lock(ws.mu);
+    // Whatever way this call ends -- also on an error after the first enqueue -- the three workspace streams are drained
+    // before the mutex is released and the caller gets its buffers back: no kernel or copy is left in flight on memory
+    // the caller may recycle (pinned output pool) or the next call may reuse (d_j, d_in).
+    struct Quiesce {
+        Workspace& w;
+        ~Quiesce() {
+            if (w.s_h2d) cudaStreamSynchronize(w.s_h2d);
+            if (w.s_compute) cudaStreamSynchronize(w.s_compute);
+            if (w.s_copy) cudaStreamSynchronize(w.s_copy);
+        }
+    } quiesce{ws};
     if (!ws.s_compute) HPEM_CUDA(cudaStreamCreateWithFlags(&ws.s_compute, cudaStreamNonBlocking));
     if (!ws.s_copy) HPEM_CUDA(cudaStreamCreateWithFlags(&ws.s_copy, cudaStreamNonBlocking));
     if (!ws.s_h2d) HPEM_CUDA(cudaStreamCreateWithFlags(&ws.s_h2d, cudaStreamNonBlocking));
@@ -771,6 +802,24 @@ int hpem_moments_layout_query(const hpem_grid* g, const hpem_moments_spec* spec,
     return moments_layout(g, spec, lay);
 }
 
+static void fill_moments_params(const hpem_moments_spec& spec, const hpem_moments_layout& lay, hpem::MomentsParams& m) {
+    std::memset(&m, 0, sizeof(m));
+    m.hist_stride = spec.hist_angle_stride;
+    m.hist_shift = 0;
+    while ((1 << m.hist_shift) < m.hist_stride) ++m.hist_shift;
+    m.want_cathode = spec.want_cathode;
+    m.hist_sub_bits = spec.hist_sub_bits;
+    m.hist_min_exp2 = spec.hist_min_exp2;
+    m.hist_max_exp2 = spec.hist_max_exp2;
+    m.n_hist_angles = lay.n_hist_angles;
+    m.n_bins = lay.n_bins;
+    m.n_sums = lay.n_sums;
+    m.off_angle_sum = lay.off_angle_sum;
+    m.off_angle_sumsq = lay.off_angle_sumsq;
+    m.off_hist = lay.off_hist;
+    for (int k = 0; k < 3; ++k) m.shift[k] = spec.scalar_shift[k];
+}
+
 static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpem::SamplerParams* sampler, double torr_2_pa,
                        const hpem_moments_spec* spec, double* sums, double* minmax, void* stream) {
     hpem_moments_layout lay;
@@ -778,41 +827,48 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
     if (rc != HPEM_OK) return rc;
     if ((!in && !sampler) || !sums || !minmax) return fail(HPEM_ERR_INVALID_ARG, "inputs/sums/minmax must be non-NULL");
     if (n < 0) return fail(HPEM_ERR_INVALID_ARG, "negative sample count");
+    if (n > (int64_t)4000000000LL) return fail(HPEM_ERR_INVALID_ARG, "at most 4e9 samples per call (32-bit histogram counters per block)");
+    for (int k = 0; k < 3; ++k)
+        if (!std::isfinite(spec->scalar_shift[k])) return fail(HPEM_ERR_INVALID_ARG, "scalar_shift[%d] must be finite", k);
     if (n == 0) return HPEM_OK;
     DeviceGuard guard(g->device);
     if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", g->device);
     using namespace hpem;
     const int n_chunks = (g->n_angles + kChunk - 1) / kChunk;
-    if (lay.n_bins > 65535) return fail(HPEM_ERR_UNSUPPORTED, "at most 65535 histogram bins per angle (got %d)", lay.n_bins);
-    // One persistent block per SM with as many warps as shared memory allows (per-warp tile + per-angle accumulators +
-    // histogram slot buffer; the block-wide histograms are paid once), several smaller blocks when few warps fit.
+    // One persistent block per SM with as many warps (<= 12, two samples per thread) as shared memory allows: per warp a
+    // 32 x 16 tile of (t, q) pairs and the per-angle accumulators.
     int dev_smem = 0;
     HPEM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, g->device));
-    const size_t smem_budget = (size_t)dev_smem - 2048;   // static shared memory of the kernel + slack
-    int warps = kMaxWarpsM;
-    while (warps > 1 && moments_smem_bytes(g->n_angles_pad, n_chunks * kChunk, lay.n_hist_angles, lay.n_bins, warps) > smem_budget) --warps;
-    const size_t smem = moments_smem_bytes(g->n_angles_pad, n_chunks * kChunk, lay.n_hist_angles, lay.n_bins, warps);
+    const size_t smem_budget = (size_t)dev_smem - 4096;   // static shared memory of the kernel + slack
+    static const int warps_env = []() { const char* v = std::getenv("HPEM_MOMENTS_WARPS"); return v ? std::atoi(v) : 0; }();
+    int warps = warps_env > 0 ? std::min(warps_env, kMaxWarpsM) : kMaxWarpsM;
+    while (warps > 1 && moments_smem_bytes(g->n_angles_pad, n_chunks * kChunk, warps) > smem_budget) --warps;
+    const size_t smem = moments_smem_bytes(g->n_angles_pad, n_chunks * kChunk, warps);
     if (smem > smem_budget)
-        return fail(HPEM_ERR_UNSUPPORTED, "histogram/angle configuration needs %zu bytes of shared memory (> %zu): "
-                    "raise hist_angle_stride or lower hist_sub_bits", smem, smem_budget);
+        return fail(HPEM_ERR_UNSUPPORTED, "%d angles need %zu bytes of shared memory (> %zu)", g->n_angles, smem, smem_budget);
     const int hs = spec->hist_angle_stride == 0 ? 0 : (spec->hist_angle_stride == 8 ? 8 : -1);
-#define HPEM_MOMENTS_SMEM(S, H) rc = set_smem(moments_kernel<S, H>, smem)
-    if (sampler) { if (hs == 0) HPEM_MOMENTS_SMEM(true, 0); else if (hs == 8) HPEM_MOMENTS_SMEM(true, 8); else HPEM_MOMENTS_SMEM(true, -1); }
-    else         { if (hs == 0) HPEM_MOMENTS_SMEM(false, 0); else if (hs == 8) HPEM_MOMENTS_SMEM(false, 8); else HPEM_MOMENTS_SMEM(false, -1); }
-#undef HPEM_MOMENTS_SMEM
-    if (rc != HPEM_OK) return rc;
+    const bool restart = n_chunks > kRestartChunks;
     const int threads = warps * 32;
-    int sm_smem = 0;
-    HPEM_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, g->device));
-    const int blocks_per_sm = std::max(1, std::min<int>({kMaxWarpsM / warps, (int)((size_t)sm_smem / (smem + 2048)), 4}));
-    const int64_t batches = (n + threads - 1) / threads;
-    const int blocks = (int)std::min<int64_t>(batches, (int64_t)g->sm_count * blocks_per_sm);
+    const int64_t batches = (n + 2 * threads - 1) / (2 * threads);
+    const int blocks = (int)std::min<int64_t>(batches, (int64_t)g->sm_count);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Workspace& ws = g->ws;
     std::lock_guard<std::mutex> lock(ws.mu);
-    rc = grow(ws.d_partials, ws.partials_cap, (size_t)g->sm_count * 4 * (size_t)lay.n_sums);
-    if (rc == HPEM_OK) rc = grow(ws.d_partial_minmax, ws.partial_minmax_cap, (size_t)g->sm_count * 4 * 6);
+    // the per-block scratch buffers are shared by every caller of this grid handle: a pass on another stream waits for the
+    // previous one to finish with them
+    if (!ws.moments_done) HPEM_CUDA(cudaEventCreateWithFlags(&ws.moments_done, cudaEventDisableTiming));
+    else HPEM_CUDA(cudaStreamWaitEvent(st, ws.moments_done, 0));
+    const size_t n_part = (size_t)kMomScalars + 2 * (size_t)g->n_angles;
+    const size_t n_hist = (size_t)lay.n_hist_angles * lay.n_bins;
+    rc = grow(ws.d_partials, ws.partials_cap, (size_t)g->sm_count * n_part);
+    if (rc == HPEM_OK) rc = grow(ws.d_partial_minmax, ws.partial_minmax_cap, (size_t)g->sm_count * 6);
     if (rc != HPEM_OK) return rc;
+    if ((size_t)g->sm_count * n_hist > ws.hist_partials_cap) {
+        HPEM_CUDA(cudaStreamSynchronize(st));          // a previous pass may still be reading the old buffer
+        rc = grow(ws.d_hist_partials, ws.hist_partials_cap, (size_t)g->sm_count * n_hist);
+        if (rc != HPEM_OK) return rc;
+        HPEM_CUDA(cudaMemsetAsync(ws.d_hist_partials, 0, ws.hist_partials_cap * sizeof(unsigned), st));
+    }
 
     hpem_outputs no_out = {};
     hpem_inputs no_in = {};
@@ -820,34 +876,60 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
     fill_params(*g, in ? *in : no_in, no_out, 0, n, torr_2_pa, p);
     p.has_thrust = spec->want_thrust != 0;
     MomentsParams m;
-    m.hist_stride = spec->hist_angle_stride;
-    m.hist_shift = 0;
-    while ((1 << m.hist_shift) < m.hist_stride) ++m.hist_shift;
-    m.want_cathode = spec->want_cathode;
-    m.hist_sub_bits = spec->hist_sub_bits;
-    m.hist_min_exp2 = spec->hist_min_exp2;
-    m.hist_max_exp2 = spec->hist_max_exp2;
-    m.n_hist_angles = lay.n_hist_angles;
-    m.n_bins = lay.n_bins;
-    m.n_sums = lay.n_sums;
-    m.off_angle_sum = lay.off_angle_sum;
-    m.off_angle_sumsq = lay.off_angle_sumsq;
-    m.off_hist = lay.off_hist;
-    m.sampled = sampler ? 1 : 0;
+    fill_moments_params(*spec, lay, m);
     m.partials = ws.d_partials;
     m.partial_minmax = ws.d_partial_minmax;
+    m.hist_partials = ws.d_hist_partials;
     SamplerParams sp_zero;
     std::memset(&sp_zero, 0, sizeof(sp_zero));
-#define HPEM_MOMENTS_LAUNCH(S, H, SP) moments_kernel<S, H><<<blocks, threads, smem, st>>>(p, m, SP)
-    if (sampler) { if (hs == 0) HPEM_MOMENTS_LAUNCH(true, 0, *sampler); else if (hs == 8) HPEM_MOMENTS_LAUNCH(true, 8, *sampler); else HPEM_MOMENTS_LAUNCH(true, -1, *sampler); }
-    else         { if (hs == 0) HPEM_MOMENTS_LAUNCH(false, 0, sp_zero); else if (hs == 8) HPEM_MOMENTS_LAUNCH(false, 8, sp_zero); else HPEM_MOMENTS_LAUNCH(false, -1, sp_zero); }
-#undef HPEM_MOMENTS_LAUNCH
+    const SamplerParams& sp = sampler ? *sampler : sp_zero;
+#define HPEM_MOMENTS_GO(S, H, R)                                        \
+    do {                                                                \
+        rc = set_smem(moments_kernel<S, H, R>, smem);                   \
+        if (rc != HPEM_OK) return rc;                                   \
+        moments_kernel<S, H, R><<<blocks, threads, smem, st>>>(p, m, sp); \
+    } while (0)
+#define HPEM_MOMENTS_GO_R(S, H) do { if (restart) HPEM_MOMENTS_GO(S, H, true); else HPEM_MOMENTS_GO(S, H, false); } while (0)
+#define HPEM_MOMENTS_GO_H(S) do { if (hs == 0) HPEM_MOMENTS_GO_R(S, 0); else if (hs == 8) HPEM_MOMENTS_GO_R(S, 8); else HPEM_MOMENTS_GO_R(S, -1); } while (0)
+    if (sampler) HPEM_MOMENTS_GO_H(true); else HPEM_MOMENTS_GO_H(false);
+#undef HPEM_MOMENTS_GO_H
+#undef HPEM_MOMENTS_GO_R
+#undef HPEM_MOMENTS_GO
     HPEM_CUDA(cudaGetLastError());
-    const int fthreads = 256;
+    const int fthreads = 128;
     moments_finalize_kernel<<<(unsigned)((lay.n_sums + fthreads - 1) / fthreads), fthreads, 0, st>>>(
-        ws.d_partials, ws.d_partial_minmax, blocks, lay.n_sums, sums, minmax);
+        ws.d_partials, ws.d_partial_minmax, ws.d_hist_partials, blocks, g->n_angles, m, sums, minmax);
+    moments_counts_kernel<<<1, 32, 0, st>>>(ws.d_partials, blocks, g->n_angles, sums);
     HPEM_CUDA(cudaGetLastError());
-    g_launches.fetch_add(2, std::memory_order_relaxed);
+    HPEM_CUDA(cudaEventRecord(ws.moments_done, st));
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    return HPEM_OK;
+}
+
+int hpem_moments_merge(int device, const hpem_moments_layout* lay, int n_parts, const double* parts, int64_t part_stride,
+                       double* sums, double* minmax, void* stream) {
+    if (!lay || !parts || !sums || !minmax) return fail(HPEM_ERR_INVALID_ARG, "NULL argument");
+    if (n_parts < 1) return fail(HPEM_ERR_INVALID_ARG, "need at least one part");
+    if (part_stride < lay->n_sums + 6) return fail(HPEM_ERR_INVALID_ARG, "part_stride %lld < n_sums + 6", (long long)part_stride);
+    const int64_t n_angles = lay->off_angle_sumsq - lay->off_angle_sum;
+    if (n_angles < 2 || lay->off_angle_sum != hpem::kMomScalars || lay->off_hist != lay->off_angle_sumsq + n_angles ||
+        lay->n_sums != lay->off_hist + (int64_t)lay->n_hist_angles * lay->n_bins)
+        return fail(HPEM_ERR_INVALID_ARG, "inconsistent moments layout");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(HPEM_ERR_CUDA, "cannot select device %d", device);
+    hpem::MomentsParams m;
+    std::memset(&m, 0, sizeof(m));
+    m.n_hist_angles = lay->n_hist_angles;
+    m.n_bins = lay->n_bins;
+    m.n_sums = lay->n_sums;
+    m.off_angle_sum = lay->off_angle_sum;
+    m.off_angle_sumsq = lay->off_angle_sumsq;
+    m.off_hist = lay->off_hist;
+    const int threads = 128;
+    hpem::moments_merge_kernel<<<(unsigned)((lay->n_sums + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        parts, part_stride, n_parts, (int)n_angles, m, sums, minmax);
+    HPEM_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return HPEM_OK;
 }
 

@@ -64,6 +64,7 @@ struct EvalParams {
     // 32-byte-aligned body element, and the common body length (multiple of 4)
     int q_lead[4], q_tail[4], q_body;
     int l2_hint;             // K1u tensor stores: 0 normal, 1 evict_last, 2 evict_first (see l2_store_policy)
+    int no_fastmath;         // 1: always take the libdevice back end for the per-sample part (HPEM_FLAG_NO_FASTMATH)
 };
 
 struct JMaps {               // tensor maps of j_ion: [0] the (n, A) view; quad-row mode: one pair per row phase
@@ -166,6 +167,9 @@ constexpr int kTmaGroupBytes = kTmaCB * kTmaTileBytes;
 constexpr int kOneBufferMaxAngles = HPEM_ONE_BUFFER_MAX_ANGLES;   // K1u: single staging buffer per warp up to this angle count
 constexpr int kOneBufferMaxAnglesQuad = 192;                      // ... in the quad-row store mode
 constexpr int kQuadMinAngles = 64;                                // quad-row store mode from this angle count on
+#ifndef HPEM_SMEM_SKEW
+#define HPEM_SMEM_SKEW 0          // test hook: shift K1u's shared-memory layout by a multiple of 128 bytes (swizzle vs alignment)
+#endif
 
 struct BeamState {  // per-thread recurrence state of one Gaussian beam
     double ec, rc, gc;     // chunk-start profile value, chunk-start ratio, chunk-to-chunk factor
@@ -173,16 +177,17 @@ struct BeamState {  // per-thread recurrence state of one Gaussian beam
     double x, amp;
 };
 
+template <bool FAST = false>
 __device__ __forceinline__ void beam_init(BeamState& b, double h, double a, double amp) {
-    const double t = h / a;
+    const double t = m_div<FAST>(h, a);
     b.x = t * t;                           // profile(i) = exp(-x i^2)
     b.amp = amp;
     // three exps; q = exp(-2x) and hh = exp(-512x) are squares of two of them.  The extra rounding (1 ulp on a factor that
     // is applied <= 16 times between exact re-anchorings) adds ~1.5e-14 to the recurrence's relative error (budget 1e-12).
-    b.rc = exp(-b.x);
+    b.rc = m_exp<FAST>(-b.x);
     b.q = b.rc * b.rc;
-    b.qk = exp(-(2.0 * kChunk) * b.x);
-    b.gc = exp(-double(kChunk * kChunk) * b.x);
+    b.qk = m_exp<FAST>(-(2.0 * kChunk) * b.x);
+    b.gc = m_exp<FAST>(-double(kChunk * kChunk) * b.x);
     b.hh = b.gc * b.gc;
     b.ec = 1.0;
 }
@@ -190,15 +195,16 @@ __device__ __forceinline__ void beam_init(BeamState& b, double h, double a, doub
 // a warp start their 32-byte-aligned body at different angles).  One code path for every offset -- no divergence -- and
 // still three exps: the offset-dependent start values are small powers of u = exp(-x) and of qk = exp(-32 x)
 // (<= 6 extra roundings, a constant ~5e-16 relative factor on the row).  `u` is returned for the lead elements.
+template <bool FAST = false>
 __device__ __forceinline__ double beam_init_offset(BeamState& b, double h, double a, double amp, int o) {
-    const double t = h / a;
+    const double t = m_div<FAST>(h, a);
     b.x = t * t;
     b.amp = amp;
-    const double u = exp(-b.x);
+    const double u = m_exp<FAST>(-b.x);
     const double u2 = u * u, u4 = u2 * u2;
     b.q = u2;
-    b.qk = exp(-(2.0 * kChunk) * b.x);
-    const double g0 = exp(-double(kChunk * kChunk) * b.x);
+    b.qk = m_exp<FAST>(-(2.0 * kChunk) * b.x);
+    const double g0 = m_exp<FAST>(-double(kChunk * kChunk) * b.x);
     b.hh = g0 * g0;
     // E(o) = u^(o^2), E(o+1)/E(o) = u^(2o+1), E(o+16)/E(o) = g0 * qk^o
     b.ec = (o == 0) ? 1.0 : (o == 1) ? u : (o == 2) ? u4 : u4 * u4 * u;
@@ -238,16 +244,24 @@ constexpr int kStoreQuad = 3;   // row pitch not a multiple of 32 bytes (A % 4 !
 // sectors: they go through a small per-warp shared-memory buffer and are written by 4-8 adjacent lanes per boundary.
 constexpr int kBsecSlots = 8;                       // <= 7 tail + 3 lead elements, always 0, 4 or 8 per row boundary
 constexpr int kBsecBytes = 32 * kBsecSlots * 8;     // per warp
+static_assert(kBsecBytes <= kTmaGroupBytes, "the row-boundary buffer aliases one staging group");
 
 // NBUF staging buffers per warp: 2 overlap the fill of one group with the TMA read of the other (best for long rows);
 // 1 halves shared memory and almost doubles the resident warps, which wins while the per-sample prologue dominates
 // (A <~ 128: 0.120 ms vs 0.148 ms at 1e6 x 64, B200)
 template <bool WANT_PLUME, bool STORE_J, int MODE, int NBUF, int THREADS = kThreadsU>
-__global__ void __launch_bounds__(THREADS, (NBUF == 1 ? 640 : 384) / THREADS)   // 20 resident warps with one staging buffer, 12 with two
+#ifndef HPEM_RES1
+#define HPEM_RES1 640
+#endif
+__global__ void __launch_bounds__(THREADS, (NBUF == 1 ? HPEM_RES1 : 384) / THREADS)   // 20 resident warps with one staging buffer, 12 with two
 eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // layout: [staging tiles (1024-byte aligned for the 128B TMA swizzle)] [row-boundary buffers (quad mode)] [fused weights]
-    unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    extern __shared__ __align__(128) unsigned char smem_u[];
+    // layout: [staging tiles] [fused weights].  The staging tiles are 128B-swizzled for the TMA engine, which XORs the
+    // 16-byte chunk index with ABSOLUTE shared-memory address bits 7..9; the writer below does the same with the row's
+    // address, so the tiles only need 128-byte alignment (no 1 KB of slack per block: at 18 KB per block an SM holds 12
+    // blocks of the short-row configuration instead of 9).  Quad mode: the row-boundary buffer aliases the staging area
+    // once the sweep's tensor stores have been read out.
+    unsigned char* smem_al = smem_u + HPEM_SMEM_SKEW;
     constexpr int kThreadsU = THREADS;           // shadow the file-level defaults: this kernel is instantiated per block size
     constexpr int kWarpsU = THREADS / 32;
     constexpr bool QUAD = (MODE == kStoreQuad);
@@ -257,18 +271,12 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
     const int stage_bytes_per_warp = USE_TMA ? NBUF * kGroupBytes
                                              : (ROWS ? ((32 * p.n_angles * 8 + 15) & ~15) : 32 * kTilePitch * 8);
     const int stage_bytes = STORE_J ? kWarpsU * stage_bytes_per_warp : 0;
-    const int bsec_bytes = (STORE_J && QUAD) ? kWarpsU * kBsecBytes : 0;
-    double2* wsm = reinterpret_cast<double2*>(smem_al + stage_bytes + bsec_bytes);
+    double2* wsm = reinterpret_cast<double2*>(smem_al + stage_bytes);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     unsigned char* stage = smem_al + warp * stage_bytes_per_warp;
-    double* bsec = reinterpret_cast<double*>(smem_al + stage_bytes + warp * kBsecBytes);   // [32 boundaries][8 slots]
-
-    if (WANT_PLUME) {
-        for (int i = threadIdx.x; i < p.n_angles_pad; i += kThreadsU) wsm[i] = p.w[i];
-        __syncthreads();
-    }
+    double* bsec = reinterpret_cast<double*>(stage);   // [32 boundaries][8 slots], after the sweep (kBsecBytes <= one staging group)
 
     // which of the warp's 32 samples this lane owns.  Quad mode: quarter-warp f (lanes 8f .. 8f+7) takes the samples of
     // phase f, lane 8f+q the one in quad-row q -- conflict-free 16-byte stores into one swizzle atom per phase
@@ -279,38 +287,64 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
     const long long s_raw = warp_s0 + lidx;
     const bool active = s_raw < p.n;
     const long long s = active ? s_raw : p.n - 1;  // inactive lanes shadow the last sample, never store
-    if (warp_s0 >= p.n) return;  // whole warp out of range (after the only __syncthreads)
 
-    // all per-sample loads are issued up front (15 independent LDG.64 in flight per thread)
+    // all per-sample loads are issued up front (15 independent LDG.64 in flight per thread), BEFORE the weights are staged:
+    // the block pays one global-memory round trip at its start, not two
     double x_in[kNumInputs];
+#ifndef HPEM_LOADS_LATE
 #pragma unroll
     for (int q = 0; q < kNumInputs; ++q) {
         const bool needed = (q == IN_P_b) || (q <= IN_P_T ? p.v_cc != nullptr : (q == IN_T ? p.t_c != nullptr : WANT_PLUME));
         x_in[q] = needed ? load_in(p, q, s) : 0.0;
     }
-    const double p_b = x_in[IN_P_b];
-
-    if (p.v_cc) {
-        const double v = cathode_vcc(p_b, x_in[IN_V_a], x_in[IN_T_e], x_in[IN_V_vac], x_in[IN_Pstar], x_in[IN_P_T], p.torr);
-        if (active) p.v_cc[s] = v;
+#endif
+    if (WANT_PLUME) {
+        const int n_w = ((p.n_angles + kChunk - 1) / kChunk) * kChunk;   // the sweep never reads a weight beyond its last chunk
+        for (int i = threadIdx.x; i < n_w; i += kThreadsU) wsm[i] = p.w[i];
+        __syncthreads();
     }
-    if (!WANT_PLUME) return;
+#ifdef HPEM_LOADS_LATE
+#pragma unroll
+    for (int q = 0; q < kNumInputs; ++q) {
+        const bool needed = (q == IN_P_b) || (q <= IN_P_T ? p.v_cc != nullptr : (q == IN_T ? p.t_c != nullptr : WANT_PLUME));
+        x_in[q] = needed ? load_in(p, q, s) : 0.0;
+    }
+#endif
+    if (warp_s0 >= p.n) return;  // whole warp out of range (after the only __syncthreads)
 
-    const SampleConsts k = plume_sample_consts(p_b, x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3], x_in[IN_c4],
-                                               x_in[IN_c5], p.torr);
-    double j_cex, base;
-    cex_terms(k.density, x_in[IN_sigma], x_in[IN_I_B0], p.radius0, j_cex, base);
-
+    // per-sample prologue (cathode.py:26-37, plume.py:40-98, recurrence start values) in one of two arithmetic back ends:
+    // branch-free (hpem_fastmath.cuh) when all 32 samples of the warp are in the nominal range, libdevice otherwise
+    const bool want_cathode = p.v_cc != nullptr;
     const int off = QUAD ? p.q_lead[phase] : 0;  // angle index of the chunked sweep's first element
+    SampleConsts k;
     BeamState b1, b2;
+    double v_cc = 0.0, j_cex = 0.0, base = 0.0;
     double u1 = 0.0, u2 = 0.0;                   // exp(-x) of the two beams (quad mode: the lead elements need E(1), E(2))
-    if (QUAD) {
-        u1 = beam_init_offset(b1, p.h, k.a1, __dmul_rn(base, k.amp1), off);
-        u2 = beam_init_offset(b2, p.h, k.a2, __dmul_rn(base, k.amp2), off);
-    } else {
-        beam_init(b1, p.h, k.a1, __dmul_rn(base, k.amp1));   // (base_density * A1), plume.py:99
-        beam_init(b2, p.h, k.a2, __dmul_rn(base, k.amp2));   // (base_density * A2), plume.py:100
-    }
+    auto prologue = [&](auto fast_tag) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        if (want_cathode)
+            v_cc = cathode_vcc<FAST>(x_in[IN_P_b], x_in[IN_V_a], x_in[IN_T_e], x_in[IN_V_vac], x_in[IN_Pstar], x_in[IN_P_T], p.torr);
+        if (WANT_PLUME) {
+            k = plume_sample_consts<FAST>(x_in[IN_P_b], x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3], x_in[IN_c4],
+                                          x_in[IN_c5], p.torr);
+            cex_terms<FAST>(k.density, x_in[IN_sigma], x_in[IN_I_B0], p.radius0, j_cex, base);
+            if (QUAD) {
+                u1 = beam_init_offset<FAST>(b1, p.h, k.a1, __dmul_rn(base, k.amp1), off);
+                u2 = beam_init_offset<FAST>(b2, p.h, k.a2, __dmul_rn(base, k.amp2), off);
+            } else {
+                beam_init<FAST>(b1, p.h, k.a1, __dmul_rn(base, k.amp1));   // (base_density * A1), plume.py:99
+                beam_init<FAST>(b2, p.h, k.a2, __dmul_rn(base, k.amp2));   // (base_density * A2), plume.py:100
+            }
+        }
+    };
+    const bool nominal = prologue_nominal(x_in, p.torr, want_cathode, WANT_PLUME, p.radius0);
+    const bool fast = __all_sync(0xffffffffu, nominal) && !p.no_fastmath;
+    if (fast)
+        prologue(std::true_type{});
+    else
+        prologue(std::false_type{});
+    if (want_cathode && active) p.v_cc[s] = v_cc;
+    if (!WANT_PLUME) return;
 
     const bool known_invalid = (k.a1 <= 0.0);  // plume.py:105 first term
     // With non-negative beam amplitudes and a positive CEX floor every j_ion is > 0 (or NaN), so the per-angle
@@ -337,18 +371,6 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
         bad |= (j <= 0.0);
         if (STORE_J) bsec[slot_row * kBsecSlots + slot] = known_invalid ? kInvalidFill : j;
     };
-    if (QUAD && off > 0) {
-        // lead elements (angles 0 .. off-1 <= 2): E(0) = 1, E(1) = u, E(2) = u^4.  They complete the sector(s) that the
-        // previous row's tail starts: boundary lidx-1, after that row's tail[phase-1] slots.
-        const int t_prev = p.q_tail[(phase + 3) & 3];
-        edge_element(b1.amp + b2.amp, 0, lidx - 1, t_prev);
-        if (off > 1) edge_element(b1.amp * u1 + b2.amp * u2, 1, lidx - 1, t_prev + 1);
-        if (off > 2) {
-            const double v1 = u1 * u1, v2 = u2 * u2;
-            edge_element(b1.amp * (v1 * v1) + b2.amp * (v2 * v2), 2, lidx - 1, t_prev + 2);
-        }
-    }
-
     auto chunk_loop = [&](auto checked_tag) {
         constexpr bool CHECKED = decltype(checked_tag)::value;
         for (int c = 0; c < n_chunks; ++c) {
@@ -368,6 +390,7 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
                      : (USE_TMA ? group_buf + (c % kTmaCB) * kTmaTileBytes + lane * (kChunk * 8)
                                 : (ROWS ? stage + (size_t(lane) * A + i0) * 8 : stage + lane * (kTilePitch * 8)));
             const double2* wrow = wsm + i0 + off;
+            const int swz = USE_TMA ? (int)((smem_u32(my_row) >> 7) & 7u) : 0;   // the TMA engine's 128B swizzle: chunk ^ address bits 7..9
             auto step = [&](double2 w, double& jout) {
                 const double sum = e1 + e2;    // j_beam + j_scat
                 const double j = sum + j_cex;  // plume.py:102
@@ -390,7 +413,7 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
                     step(wrow[kk + 1], jb);
                     if (STORE_J) {
                         if (USE_TMA) {
-                            *reinterpret_cast<double2*>(my_row + ((((kk >> 1) ^ (prl & 7))) << 4)) = make_double2(ja, jb);
+                            *reinterpret_cast<double2*>(my_row + (((kk >> 1) ^ swz) << 4)) = make_double2(ja, jb);
                         } else {
                             reinterpret_cast<double*>(my_row)[kk] = ja;
                             reinterpret_cast<double*>(my_row)[kk + 1] = jb;
@@ -403,7 +426,7 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
                     step(wrow[kk], ja);
                     if (STORE_J) {
                         if (USE_TMA)
-                            *reinterpret_cast<double*>(my_row + ((((kk >> 1) ^ (prl & 7))) << 4) + ((kk & 1) << 3)) = ja;
+                            *reinterpret_cast<double*>(my_row + (((kk >> 1) ^ swz) << 4) + ((kk & 1) << 3)) = ja;
                         else
                             reinterpret_cast<double*>(my_row)[kk] = ja;
                     }
@@ -476,6 +499,21 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
         chunk_loop(std::false_type{});
 
     if (QUAD) {
+        if (STORE_J) {   // the row-boundary buffer aliases the staging area: every tensor store must have read its tile
+            if (lane < 4) tma_wait_read<0>();
+            __syncwarp();
+        }
+        if (off > 0) {
+            // lead elements (angles 0 .. off-1 <= 2): E(0) = 1, E(1) = u, E(2) = u^4.  They complete the sector(s) that the
+            // previous row's tail starts: boundary lidx-1, after that row's tail[phase-1] slots.
+            const int t_prev = p.q_tail[(phase + 3) & 3];
+            edge_element(b1.amp + b2.amp, 0, lidx - 1, t_prev);
+            if (off > 1) edge_element(b1.amp * u1 + b2.amp * u2, 1, lidx - 1, t_prev + 1);
+            if (off > 2) {
+                const double v1 = u1 * u1, v2 = u2 * u2;
+                edge_element(b1.amp * (v1 * v1) + b2.amp * (v2 * v2), 2, lidx - 1, t_prev + 2);
+            }
+        }
         // tail elements (angles off + q_body .. A-1, at most 7): the recurrence simply continues.  They open the
         // sector(s) that the next row's lead completes: boundary lidx, slots 0 .. tail-1.
         const int n_tail = p.q_tail[phase];
@@ -531,11 +569,18 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
     }
 
     // per-sample epilogue: plume.py:124-127,137 (NOT masked by `invalid`)
-    double cd = num / den;
-    if (cd == CUDART_INF) cd = CUDART_NAN;  // plume.py:125
+    double cd, dv;
+    if (fast && __all_sync(0xffffffffu, fm_mid(den) && fm_mid0(num))) {
+        cd = fm_div(num, den);
+        dv = fm_acos(cd);
+    } else {
+        cd = num / den;
+        if (cd == CUDART_INF) cd = CUDART_NAN;  // plume.py:125
+        dv = acos(cd);
+    }
     const bool invalid = known_invalid || bad;
     if (active) {
-        if (p.div_angle) p.div_angle[s] = acos(cd);
+        if (p.div_angle) p.div_angle[s] = dv;
         if (p.cos_div) p.cos_div[s] = cd;
         if (p.t_c) p.t_c[s] = __dmul_rn(x_in[IN_T], cd);
         if (p.invalid) p.invalid[s] = invalid ? 1 : 0;
@@ -1312,359 +1357,6 @@ __global__ void __launch_bounds__(kThreadsD) eval_direct_kernel(const EvalParams
                 __stcs(row + cidx, __dadd_rn(__dadd_rn(jb, js), j_cex));
             }
         }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2: reduce-only Monte-Carlo pass (no j_ion materialisation) -- sample moments and histograms
-// ---------------------------------------------------------------------------------------------
-// Same per-sample arithmetic and the same one-lane recurrence sweep as K1u, but instead of storing j_ion the
-// 32 samples x 16 angles tile is column-reduced in shared memory: per angle sum(j), sum(j^2) over samples, plus
-// log-linear histograms of j for every `hist_stride`-th angle (bin index = leading bits of the fp64 pattern: 2^sub_bits
-// bins per octave, no log10 evaluation).  Per-sample scalars (V_cc, div_angle, T_c) accumulate in registers.
-// Persistent blocks stride over the sample batches and emit ONE partial vector per block; a second kernel adds the
-// partials in block order, so results are bit-reproducible for a fixed launch geometry.  The packed result is what
-// the multi-GPU driver all-reduces (ncclSum over fp64; counts are stored as fp64, exact below 2^53).
-struct MomentsParams {
-    int hist_stride;      // power of two, 0 = no histograms
-    int hist_shift;       // log2(hist_stride)
-    int want_cathode;     // accumulate V_cc moments (the six cathode inputs are read)
-    int hist_sub_bits;
-    int hist_min_exp2, hist_max_exp2;
-    int n_hist_angles, n_bins;
-    long long n_sums;     // doubles per partial vector
-    long long off_angle_sum, off_angle_sumsq, off_hist;
-    int sampled;          // 1: inputs are drawn on the fly by the on-device sampler (no input arrays are read)
-    double* partials;     // [gridDim.x][n_sums]
-    double* partial_minmax;  // [gridDim.x][6]  (-min, max) x (V_cc, div_angle, T_c)
-};
-constexpr int kMomScalars = 12;  // n_samples n_invalid n_nonfinite_rows | {n_finite sum sumsq} x {V_cc div_angle T_c}
-#ifndef HPEM_THREADS_M
-#define HPEM_THREADS_M 512
-#endif
-constexpr int kThreadsM = HPEM_THREADS_M;   // upper bound; the launch picks the warp count that fits shared memory
-constexpr int kMaxWarpsM = kThreadsM / 32;
-constexpr int kHbufPitch = 34;              // u16 bin indices, [32 samples][32 slots] + 2: row pitch of 17 words (odd)
-constexpr unsigned short kHbufSkip = 0xFFFFu;
-
-__host__ __device__ inline int moments_hist_pitch(int n_bins) { return n_bins | 1; }   // odd row pitch of the shared histograms
-// shared memory of one block with `warps` warps
-__host__ __device__ inline size_t moments_smem_bytes(int n_angles_pad, int a_pad, int n_hist_angles, int n_bins, int warps) {
-    return size_t(n_angles_pad) * sizeof(double2) + size_t(warps) * 32 * kTilePitch * sizeof(double) +
-           size_t(warps) * a_pad * 2 * sizeof(double) + size_t(n_hist_angles) * moments_hist_pitch(n_bins) * sizeof(unsigned) +
-           (n_hist_angles > 0 ? size_t(warps) * 32 * kHbufPitch * sizeof(unsigned short) : 0);
-}
-
-__device__ __forceinline__ int hist_bin(double j, const MomentsParams& m) {
-    // log-linear bin: octave from the exponent field, 2^sub_bits linear sub-bins from the leading mantissa bits.
-    // bin 0 = underflow (incl. zero/negative), n_bins-1 = overflow (incl. +inf); NaN rows never get here.
-    const int hi = __double2hiint(j);
-    if (hi < 0) return 0;
-    const int key = hi >> (20 - m.hist_sub_bits);                        // (biased exponent << sub_bits) | sub-bin
-    const int lo_key = (m.hist_min_exp2 + 1023) << m.hist_sub_bits;
-    const int b = key - lo_key + 1;
-    return min(max(b, 0), m.n_bins - 1);
-}
-
-// Histograms: a sample's bin index at every histogrammed angle is parked in a per-warp [32 samples][32 slots] u16 buffer
-// while the sweep runs; when 32 slots are full (or the sweep ends) lane a takes slot a and walks the 32 samples, so the
-// lanes of one warp never hit the same counter (different angles = different histogram rows, odd row pitch = different
-// banks).  The thread-per-sample alternative -- all 32 lanes incrementing the histogram of ONE angle -- serialises on
-// the few bins a population occupies at a given angle (measured: 44 % of the kernel at 1 histogram per 8 angles).
-__device__ __forceinline__ void hist_flush(unsigned* hist, const unsigned short* hbuf, int lane, int slot_base, int n_slots,
-                                           int pitch) {
-    __syncwarp();
-    if (lane < n_slots) {
-        unsigned* row = hist + (slot_base + lane) * pitch;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-            const unsigned short b = hbuf[r * kHbufPitch + lane];
-            if (b != kHbufSkip) atomicAdd(row + b, 1u);
-        }
-    }
-    __syncwarp();
-}
-
-// HS: histogram angle stride known at compile time (8, the default: the two histogrammed angles of a chunk are binned
-// straight from registers inside the unrolled sweep), 0 = no histograms, -1 = any stride (bins read back from the tile)
-template <bool SAMPLED, int HS>
-__global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams p, const MomentsParams m,
-                                                               const __grid_constant__ SamplerParams sp) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int A = p.n_angles;
-    const int n_chunks = (A + kChunk - 1) / kChunk;
-    const int a_pad = n_chunks * kChunk;
-    const int n_warps = blockDim.x >> 5;
-    const int hpitch = moments_hist_pitch(m.n_bins);
-    double2* wsm = reinterpret_cast<double2*>(smem_raw);                               // [n_angles_pad]
-    double* tiles = reinterpret_cast<double*>(wsm + p.n_angles_pad);                   // [warps][32][17]
-    double* acc_all = tiles + n_warps * 32 * kTilePitch;                               // [warps][a_pad][2]
-    unsigned* hist = reinterpret_cast<unsigned*>(acc_all + n_warps * a_pad * 2);       // [n_hist_angles][hpitch]
-    unsigned short* hbuf_all = reinterpret_cast<unsigned short*>(hist + m.n_hist_angles * hpitch);   // [warps][32][34]
-    __shared__ double red[kMaxWarpsM][kMomScalars + 6];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* tile = tiles + warp * 32 * kTilePitch;
-    double* acc = acc_all + warp * a_pad * 2;
-    unsigned short* hbuf = hbuf_all + warp * 32 * kHbufPitch;
-    for (int i = threadIdx.x; i < p.n_angles_pad; i += blockDim.x) wsm[i] = p.w[i];
-    for (int i = threadIdx.x; i < n_warps * a_pad * 2; i += blockDim.x) acc_all[i] = 0.0;
-    for (int i = threadIdx.x; i < m.n_hist_angles * hpitch; i += blockDim.x) hist[i] = 0u;
-    __syncthreads();
-
-    double sc[kMomScalars];
-#pragma unroll
-    for (int i = 0; i < kMomScalars; ++i) sc[i] = 0.0;
-    double mm[6] = {-CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF};
-    const bool want_cathode = m.want_cathode != 0;
-    const bool want_thrust = p.has_thrust;
-    const int col = lane & (kChunk - 1), half = lane >> 4;
-    const bool hist_any = m.hist_stride > 0;
-    const int h_stride = max(m.hist_stride, 1), h_shift = 20 - m.hist_sub_bits, h_last = m.n_bins - 1;
-    const int h_lo_key = ((m.hist_min_exp2 + 1023) << m.hist_sub_bits) - 1;
-
-    for (long long b0 = (long long)blockIdx.x * blockDim.x; b0 < p.n; b0 += (long long)gridDim.x * blockDim.x) {
-        const long long s_raw = b0 + threadIdx.x;
-        const bool active = s_raw < p.n;
-        const long long s = active ? s_raw : p.n - 1;
-        if (b0 + warp * 32 >= p.n) continue;   // warp-uniform; no block-level barrier inside the loop
-
-        double x_in[kNumInputs];
-        if (SAMPLED) {
-            sample_inputs(sp, (unsigned long long)s, x_in);
-        } else {
-#pragma unroll
-            for (int q = 0; q < kNumInputs; ++q) {
-                const bool needed = (q == IN_P_b) || (q <= IN_P_T ? want_cathode : (q == IN_T ? want_thrust : true));
-                x_in[q] = needed ? load_in(p, q, s) : 0.0;
-            }
-        }
-        const double thrust = x_in[IN_T];
-        if (want_cathode) {
-            const double v = cathode_vcc(x_in[IN_P_b], x_in[IN_V_a], x_in[IN_T_e], x_in[IN_V_vac], x_in[IN_Pstar],
-                                         x_in[IN_P_T], p.torr);
-            if (active && v == v) {
-                sc[3] += 1.0; sc[4] += v; sc[5] = fma(v, v, sc[5]);
-                mm[0] = fmax(mm[0], -v); mm[1] = fmax(mm[1], v);
-            }
-        }
-        const SampleConsts k = plume_sample_consts(x_in[IN_P_b], x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3],
-                                                   x_in[IN_c4], x_in[IN_c5], p.torr);
-        double j_cex, base;
-        cex_terms(k.density, x_in[IN_sigma], x_in[IN_I_B0], p.radius0, j_cex, base);
-        BeamState b1, b2;
-        beam_init(b1, p.h, k.a1, __dmul_rn(base, k.amp1));
-        beam_init(b2, p.h, k.a2, __dmul_rn(base, k.amp2));
-        const bool known_invalid = (k.a1 <= 0.0);
-        // a row is non-finite iff one of its per-sample constants is (then every angle is NaN/inf): it is counted and
-        // contributes zeros to the per-angle sums; finite rows never produce a non-finite j_ion
-        const double probe = (b1.amp + b2.amp + j_cex) * 0.0 + (b1.x + b2.x) * 0.0;
-        const bool row_ok = active && (known_invalid ||   // alpha1 <= 0: the row is the finite 1e-20 fill whatever else is NaN
-                                       ((probe == 0.0) && !(b1.x == CUDART_INF) && !(b2.x == CUDART_INF)));
-        // plume.py:105-106: a sample with alpha1 <= 0 or any j_ion <= 0 has its whole row replaced by 1e-20.  Whether
-        // a non-positive j_ion exists must be known BEFORE the row is accumulated, so the (rare) samples that can have
-        // one -- negative amplitude or no CEX floor -- run a look-ahead sweep first.
-        bool invalid = known_invalid;
-        if (!known_invalid && !(b1.amp >= 0.0 && b2.amp >= 0.0 && j_cex > 0.0)) {
-            BeamState t1 = b1, t2 = b2;
-            bool any_bad = false;
-            for (int c = 0; c < n_chunks; ++c) {
-                const int i0 = c * kChunk;
-                if (c != 0 && (c % kRestartChunks) == 0) {
-                    beam_restart(t1, i0);
-                    beam_restart(t2, i0);
-                }
-                double e1 = t1.amp * t1.ec, e2 = t2.amp * t2.ec, r1 = t1.rc, r2 = t2.rc;
-                for (int kk = 0; kk < kChunk && i0 + kk < A; ++kk) {
-                    any_bad |= ((e1 + e2) + j_cex <= 0.0);
-                    e1 *= r1; r1 *= t1.q;
-                    e2 *= r2; r2 *= t2.q;
-                }
-                beam_next_chunk(t1);
-                beam_next_chunk(t2);
-            }
-            invalid = any_bad;
-        }
-        double num = 0.0, den = 0.0;
-        if (!row_ok) {   // non-finite (or inactive shadow) row: contribute exact zeros to the per-angle sums, NaN to cos_div
-            b1.amp = b2.amp = 0.0;
-            b1.ec = b1.rc = b1.gc = b1.q = b1.qk = b1.hh = 1.0;
-            b2.ec = b2.rc = b2.gc = b2.q = b2.qk = b2.hh = 1.0;
-            b1.x = b2.x = 0.0;
-            j_cex = 0.0;
-        }
-        const double j_fill = row_ok ? kInvalidFill : 0.0;
-        double* my_row = tile + lane * kTilePitch;
-        // warps whose 32 rows are all ordinary (finite, valid) -- virtually all of them -- skip the per-element selects
-        const bool plain = !__any_sync(0xffffffffu, invalid || !row_ok);
-        int hslot = 0, hslot_base = 0;   // warp-uniform: filled slots of the histogram buffer, histogram row of slot 0
-
-        for (int c = 0; c < n_chunks; ++c) {
-            const int i0 = c * kChunk;
-            if (c != 0 && (c % kRestartChunks) == 0 && row_ok) {
-                beam_restart(b1, i0);
-                beam_restart(b2, i0);
-            }
-            double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec;
-            double r1 = b1.rc, r2 = b2.rc;
-            constexpr int kHj = HS > 0 ? kChunk / HS : 1;
-            double hj[kHj];                              // j at the histogrammed angles of this chunk (HS > 0)
-            if (plain) {
-#pragma unroll
-                for (int kk = 0; kk < kChunk; ++kk) {
-                    const double2 w = wsm[i0 + kk];      // zero beyond A
-                    const double sum = e1 + e2;
-                    den = fma(w.x, sum, den);
-                    num = fma(w.y, sum, num);
-                    const double jv = sum + j_cex;       // the value current_density() returns (columns >= A are never read back)
-                    my_row[kk] = jv;
-                    if (HS > 0 && kk % (HS > 0 ? HS : 1) == 0) hj[kk / (HS > 0 ? HS : 1)] = jv;
-                    e1 *= r1; r1 *= b1.q;
-                    e2 *= r2; r2 *= b2.q;
-                }
-            } else {
-#pragma unroll
-                for (int kk = 0; kk < kChunk; ++kk) {
-                    const double2 w = wsm[i0 + kk];
-                    const double sum = e1 + e2;
-                    den = fma(w.x, sum, den);
-                    num = fma(w.y, sum, num);
-                    const double jv = invalid ? j_fill : sum + j_cex;
-                    my_row[kk] = jv;
-                    if (HS > 0 && kk % (HS > 0 ? HS : 1) == 0) hj[kk / (HS > 0 ? HS : 1)] = jv;
-                    e1 *= r1; r1 *= b1.q;
-                    e2 *= r2; r2 *= b2.q;
-                }
-            }
-            beam_next_chunk(b1);
-            beam_next_chunk(b2);
-            // histogram bins of the selected angles of this chunk -> slot buffer (own row; the angle is warp-uniform)
-            if (HS > 0) {
-#pragma unroll
-                for (int e = 0; e < kHj; ++e) {
-                    if (i0 + e * HS < A) {
-                        const int hi = __double2hiint(hj[e]);
-                        const int b = hi < 0 ? 0 : min(max((hi >> h_shift) - h_lo_key, 0), h_last);
-                        hbuf[lane * kHbufPitch + hslot] = row_ok ? (unsigned short)b : kHbufSkip;
-                        if (++hslot == 32) {
-                            hist_flush(hist, hbuf, lane, hslot_base, 32, hpitch);
-                            hslot_base += 32;
-                            hslot = 0;
-                        }
-                    }
-                }
-            } else if (HS < 0 && hist_any) {
-                const int i_end = min(i0 + kChunk, A);
-                for (int i = (i0 + h_stride - 1) & ~(h_stride - 1); i < i_end; i += h_stride) {
-                    // log-linear bin from the leading bits of the fp64 pattern (see hist_bin)
-                    const int hi = __double2hiint(my_row[i - i0]);
-                    const int b = hi < 0 ? 0 : min(max((hi >> h_shift) - h_lo_key, 0), h_last);
-                    hbuf[lane * kHbufPitch + hslot] = row_ok ? (unsigned short)b : kHbufSkip;
-                    if (++hslot == 32) {
-                        hist_flush(hist, hbuf, lane, hslot_base, 32, hpitch);
-                        hslot_base += 32;
-                        hslot = 0;
-                    }
-                }
-            }
-            __syncwarp();
-            // column sums over the warp's 32 samples: 2 lanes per angle, 16 rows each (two independent chains per sum)
-            {
-                double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
-                const double* tcol = tile + (half * 16) * kTilePitch + col;
-#pragma unroll
-                for (int rr = 0; rr < 16; rr += 2) {
-                    const double va = tcol[rr * kTilePitch], vb = tcol[(rr + 1) * kTilePitch];
-                    s1a += va;
-                    s1b += vb;
-                    s2a = fma(va, va, s2a);
-                    s2b = fma(vb, vb, s2b);
-                }
-                double s1 = s1a + s1b, s2 = s2a + s2b;
-                s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-                if (half == 0) {
-                    acc[(i0 + col) * 2 + 0] += s1;
-                    acc[(i0 + col) * 2 + 1] += s2;
-                }
-            }
-            __syncwarp();
-        }
-        if (HS != 0 && hist_any && hslot > 0) hist_flush(hist, hbuf, lane, hslot_base, hslot, hpitch);
-        double cd = num / den;
-        if (cd == CUDART_INF) cd = CUDART_NAN;
-        if (active) {
-            sc[0] += 1.0;
-            if (invalid) sc[1] += 1.0;
-            if (!row_ok) sc[2] += 1.0;
-            const double dv = acos(cd);
-            if (dv == dv) {
-                sc[6] += 1.0; sc[7] += dv; sc[8] = fma(dv, dv, sc[8]);
-                mm[2] = fmax(mm[2], -dv); mm[3] = fmax(mm[3], dv);
-            }
-            if (want_thrust) {
-                const double tc = __dmul_rn(thrust, cd);
-                if (tc == tc) {
-                    sc[9] += 1.0; sc[10] += tc; sc[11] = fma(tc, tc, sc[11]);
-                    mm[4] = fmax(mm[4], -tc); mm[5] = fmax(mm[5], tc);
-                }
-            }
-        }
-    }
-    // ---- block reduction of the register accumulators, then one partial vector per block ----
-#pragma unroll
-    for (int i = 0; i < kMomScalars; ++i) {
-        double v = sc[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) red[warp][i] = v;
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        double v = mm[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (lane == 0) red[warp][kMomScalars + i] = v;
-    }
-    __syncthreads();
-    double* out = m.partials + (long long)blockIdx.x * m.n_sums;
-    if (threadIdx.x < kMomScalars) {
-        double v = 0.0;
-        for (int w = 0; w < n_warps; ++w) v += red[w][threadIdx.x];
-        out[threadIdx.x] = v;
-    } else if (threadIdx.x < kMomScalars + 6) {
-        double v = -CUDART_INF;
-        for (int w = 0; w < n_warps; ++w) v = fmax(v, red[w][threadIdx.x]);
-        m.partial_minmax[(long long)blockIdx.x * 6 + (threadIdx.x - kMomScalars)] = v;
-    }
-    for (int i = threadIdx.x; i < A; i += blockDim.x) {
-        double s1 = 0.0, s2 = 0.0;
-        for (int w = 0; w < n_warps; ++w) {
-            s1 += acc_all[(w * a_pad + i) * 2 + 0];
-            s2 += acc_all[(w * a_pad + i) * 2 + 1];
-        }
-        out[m.off_angle_sum + i] = s1;
-        out[m.off_angle_sumsq + i] = s2;
-    }
-    for (int i = threadIdx.x; i < m.n_hist_angles * m.n_bins; i += blockDim.x) {
-        const int a = i / m.n_bins, b = i - a * m.n_bins;
-        out[m.off_hist + i] = double(hist[a * hpitch + b]);
-    }
-}
-
-// sums[i] += sum over blocks (fixed order) of partials[b][i];  minmax[i] = max(minmax[i], max_b partial_minmax[b][i])
-__global__ void moments_finalize_kernel(const double* __restrict__ partials, const double* __restrict__ partial_minmax,
-                                        int n_blocks, long long n_sums, double* __restrict__ sums, double* __restrict__ minmax) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_sums) {
-        double v = 0.0;
-        for (int b = 0; b < n_blocks; ++b) v += partials[(long long)b * n_sums + i];
-        sums[i] += v;
-    }
-    if (i < 6 && minmax) {
-        double v = minmax[i];
-        for (int b = 0; b < n_blocks; ++b) v = fmax(v, partial_minmax[(long long)b * 6 + i]);
-        minmax[i] = v;
     }
 }
 

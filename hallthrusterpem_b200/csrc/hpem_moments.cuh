@@ -1,0 +1,494 @@
+// hpem_moments.cuh -- K2: reduce-only Monte-Carlo pass (no j_ion materialisation): sample moments and histograms.
+//
+// What the consumers of the reference's outputs compute over the sample axis (np.percentile / means of j_ion per angle,
+// tests/test_plume.py:50-52, scripts/gen_data.py:402-404) for sample counts whose j_ion cannot be stored (BASELINE
+// configs 4-5: 1e8-1e9 samples x up to 512 angles).
+//
+// Mapping.  One persistent block per SM; every THREAD owns TWO samples (s, s + 32) and runs their recurrence sweeps
+// (same arithmetic as K1u) interleaved: four independent multiply chains per thread, and the per-sample prologue of both
+// samples is one branch-free block (hpem_fastmath.cuh) that the compiler schedules as ~14 independent exp/log/division
+// chains.  The per-angle sums over samples need a transposition (thread = sample for the sweep and the quadrature,
+// thread = angle for the column sums).  The two samples of a thread are combined in registers first,
+//        t = jA + jB,   q = jA^2 + jB^2,
+// so the 32 x 16 tile that goes through shared memory holds one (t, q) pair per TWO evaluations: 16-byte conflict-free
+// stores, 16-byte column loads, half the shared-memory traffic of a value-per-evaluation tile (the first version was as
+// busy on the shared-memory pipe as on the fp64 pipe).  Column sums: 2 lanes per angle, 16 rows each, added into
+// per-warp accumulators; one partial vector per block at the end, merged in block order by moments_finalize_kernel
+// (bit-reproducible for a fixed launch geometry).
+//
+// Histograms: log-linear bins straight from the leading bits of the fp64 pattern (no log).  The 32 lanes of a warp
+// look at the SAME angle, and a population occupies few bins there, so lane-wise atomics would serialise; instead
+// __match_any_sync groups the lanes by bin and the lowest lane of each group adds the group size with ONE reduction
+// to the block's private histogram in global memory (L2 atomics; blocks never share a line).
+//
+// Second moments are kept CENTRED: a block's raw sums become (n, S, M2 = Q - S^2/n) and are merged with Chan's
+// pairwise update, block after block, call after call, rank after rank -- the variance of the whole population never
+// comes from E[x^2] - E[x]^2.  The per-sample scalars are accumulated about a caller-supplied shift.
+#pragma once
+#include "hpem_kernels.cuh"
+
+namespace hpem {
+
+struct MomentsParams {
+    int hist_stride;      // power of two, 0 = no histograms
+    int hist_shift;       // log2(hist_stride)
+    int want_cathode;     // accumulate V_cc moments (the six cathode inputs are read)
+    int hist_sub_bits;
+    int hist_min_exp2, hist_max_exp2;
+    int n_hist_angles, n_bins;
+    long long n_sums;     // doubles in the packed vector
+    long long off_angle_sum, off_angle_sumsq, off_hist;
+    double shift[3];      // V_cc, div_angle, T_c are accumulated as (x - shift)
+    double* partials;     // [gridDim.x][n_part]   n_part = kMomScalars + 2 A   (raw sums of one block)
+    double* partial_minmax;  // [gridDim.x][6]  (-min, max) x (V_cc, div_angle, T_c)
+    unsigned* hist_partials; // [gridDim.x][n_hist_angles][n_bins]   zero on entry, re-zeroed by the finalize kernel
+};
+constexpr int kMomScalars = 12;  // n_samples n_invalid n_nonfinite_rows | {n_finite sum M2} x {V_cc div_angle T_c}
+#ifndef HPEM_THREADS_M
+#define HPEM_THREADS_M 384
+#endif
+constexpr int kThreadsM = HPEM_THREADS_M;   // upper bound; the launch picks the warp count that fits shared memory
+constexpr int kMaxWarpsM = kThreadsM / 32;
+constexpr int kPairPitch = 17;              // double2 per tile row: odd -> conflict-free 16-byte stores and column loads
+
+// shared memory of one block with `warps` warps: fused weights + per-warp (t, q) tile + per-warp per-angle accumulators
+__host__ __device__ inline size_t moments_smem_bytes(int n_angles_pad, int a_pad, int warps) {
+    return size_t(n_angles_pad) * sizeof(double2) + size_t(warps) * 32 * kPairPitch * sizeof(double2) +
+           size_t(warps) * a_pad * sizeof(double2);
+}
+
+// recurrence state of one beam of one sample (same arithmetic as K1u's BeamState, so K2's j_ion is K1u's bit for bit)
+struct SweepBeam {
+    double ec, rc, gc, q, qk, hh;
+};
+
+template <bool FAST>
+__device__ __forceinline__ void sweep_beam_init(SweepBeam& b, double& x, double h, double a) {
+    const double t = m_div<FAST>(h, a);
+    x = t * t;
+    b.rc = m_exp<FAST>(-x);
+    b.q = b.rc * b.rc;
+    b.qk = m_exp<FAST>(-(2.0 * kChunk) * x);
+    b.gc = m_exp<FAST>(-double(kChunk * kChunk) * x);
+    b.hh = b.gc * b.gc;
+    b.ec = 1.0;
+}
+__device__ __forceinline__ void sweep_beam_restart(SweepBeam& b, double x, int i0) {
+    const double di = double(i0);
+    b.ec = exp(-x * (di * di));
+    b.rc = exp(-x * (2.0 * di + 1.0));
+    b.gc = exp(-x * (2.0 * kChunk * di + double(kChunk * kChunk)));
+}
+__device__ __forceinline__ void sweep_beam_next(SweepBeam& b) {
+    b.ec *= b.gc;
+    b.gc *= b.hh;
+    b.rc *= b.qk;
+}
+
+// one histogram update of the warp: lanes with the same bin elect their lowest lane, which adds the group size
+__device__ __forceinline__ void hist_add(unsigned* hrow, double j, bool ok, int lane, int h_shift, int h_lo_key, int h_last) {
+    // log-linear bin: octave from the exponent field, 2^sub_bits linear sub-bins from the leading mantissa bits.
+    // bin 0 = underflow (incl. zero/negative: the shifted pattern is negative), last bin = overflow (incl. +inf)
+    const int b = min(max((__double2hiint(j) >> h_shift) - h_lo_key, 0), h_last);
+    const unsigned peers = __match_any_sync(0xffffffffu, ok ? b : -1);
+    if (ok && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(hrow + b, (unsigned)__popc(peers));
+}
+
+// HS: histogram angle stride known at compile time (8, the default), 0 = no histograms, -1 = any power-of-two stride.
+// RESTART: the row is longer than kRestartChunks chunks, the recurrences are re-anchored with exact exps (A > 256).
+template <bool SAMPLED, int HS, bool RESTART>
+__global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams p, const MomentsParams m,
+                                                               const __grid_constant__ SamplerParams sp) {
+    extern __shared__ __align__(16) unsigned char smem_m[];
+    const int A = p.n_angles;
+    const int n_chunks = (A + kChunk - 1) / kChunk;
+    const int a_pad = n_chunks * kChunk;
+    const int n_warps = blockDim.x >> 5;
+    double2* wsm = reinterpret_cast<double2*>(smem_m);                      // [n_angles_pad]
+    double2* tiles = wsm + p.n_angles_pad;                                  // [warps][32][kPairPitch]
+    double2* acc_all = tiles + n_warps * 32 * kPairPitch;                   // [warps][a_pad]
+    __shared__ double red[kMaxWarpsM][kMomScalars + 6];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2* tile = tiles + warp * 32 * kPairPitch;
+    double2* acc = acc_all + warp * a_pad;
+    for (int i = threadIdx.x; i < p.n_angles_pad; i += blockDim.x) wsm[i] = p.w[i];
+    for (int i = threadIdx.x; i < n_warps * a_pad; i += blockDim.x) acc_all[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+
+    // per-thread accumulators of the per-sample scalars: counts as integers, sums about the caller's shift
+    int c_samples = 0, c_invalid = 0, c_nonfinite = 0, c_v = 0, c_d = 0, c_t = 0;
+    double s_v = 0.0, q_v = 0.0, s_d = 0.0, q_d = 0.0, s_t = 0.0, q_t = 0.0;
+    double mm[6] = {-CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF};
+    const bool want_cathode = m.want_cathode != 0;
+    const bool want_thrust = p.has_thrust;
+    const int col = lane & (kChunk - 1), half = lane >> 4;
+    const int h_shift = 20 - m.hist_sub_bits, h_last = m.n_bins - 1;
+    const int h_lo_key = ((m.hist_min_exp2 + 1023) << m.hist_sub_bits) - 1;
+    const int h_mask = max(m.hist_stride, 1) - 1;
+    unsigned* hist_blk = m.hist_partials + (size_t)blockIdx.x * m.n_hist_angles * m.n_bins;
+
+    const long long batch = (long long)n_warps * 64;
+    for (long long b0 = (long long)blockIdx.x * batch; b0 < p.n; b0 += (long long)gridDim.x * batch) {
+        const long long w0 = b0 + warp * 64;
+        if (w0 >= p.n) continue;   // warp-uniform; no block-level barrier inside the loop
+
+        // ---- the two samples of this thread: inputs ----
+        double x_in[2][kNumInputs];
+        bool active[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long long s_raw = w0 + u * 32 + lane;
+            active[u] = s_raw < p.n;
+            const long long s = active[u] ? s_raw : p.n - 1;   // inactive lanes shadow the last sample, contribute nothing
+            if (SAMPLED) {
+                sample_inputs(sp, (unsigned long long)s, x_in[u]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < kNumInputs; ++q) {
+                    const bool needed = (q == IN_P_b) || (q <= IN_P_T ? want_cathode : (q == IN_T ? want_thrust : true));
+                    x_in[u][q] = needed ? load_in(p, q, s) : 0.0;
+                }
+            }
+        }
+        // ---- per-sample prologue, both samples in one basic block ----
+        SweepBeam b1[2], b2[2];
+        double bx1[2], bx2[2], bamp1[2], bamp2[2];     // recurrence exponents / amplitudes (restarts, row checks)
+        double v_cc[2] = {0.0, 0.0}, j_cex[2], a1v[2];
+        auto prologue = [&](auto fast_tag) {
+            constexpr bool FAST = decltype(fast_tag)::value;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (want_cathode)
+                    v_cc[u] = cathode_vcc<FAST>(x_in[u][IN_P_b], x_in[u][IN_V_a], x_in[u][IN_T_e], x_in[u][IN_V_vac],
+                                                x_in[u][IN_Pstar], x_in[u][IN_P_T], p.torr);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const SampleConsts k = plume_sample_consts<FAST>(x_in[u][IN_P_b], x_in[u][IN_c0], x_in[u][IN_c1], x_in[u][IN_c2],
+                                                                 x_in[u][IN_c3], x_in[u][IN_c4], x_in[u][IN_c5], p.torr);
+                double base;
+                cex_terms<FAST>(k.density, x_in[u][IN_sigma], x_in[u][IN_I_B0], p.radius0, j_cex[u], base);
+                a1v[u] = k.a1;
+                bamp1[u] = __dmul_rn(base, k.amp1);
+                bamp2[u] = __dmul_rn(base, k.amp2);
+                sweep_beam_init<FAST>(b1[u], bx1[u], p.h, k.a1);
+                sweep_beam_init<FAST>(b2[u], bx2[u], p.h, k.a2);
+            }
+        };
+        const bool nominal = prologue_nominal(x_in[0], p.torr, want_cathode, true, p.radius0) &&
+                             prologue_nominal(x_in[1], p.torr, want_cathode, true, p.radius0);
+        const bool fast = __all_sync(0xffffffffu, nominal) && !p.no_fastmath;
+        if (fast)
+            prologue(std::true_type{});
+        else
+            prologue(std::false_type{});
+
+        bool invalid[2], row_ok[2];
+        double thrust[2], num[2] = {0.0, 0.0}, den[2] = {0.0, 0.0}, j_fill[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            thrust[u] = x_in[u][IN_T];
+            if (want_cathode && active[u] && v_cc[u] == v_cc[u]) {
+                const double d = v_cc[u] - m.shift[0];
+                c_v += 1; s_v += d; q_v = fma(d, d, q_v);
+                mm[0] = fmax(mm[0], -v_cc[u]); mm[1] = fmax(mm[1], v_cc[u]);
+            }
+            const bool known_invalid = (a1v[u] <= 0.0);   // plume.py:105 first term
+            // a row is non-finite iff one of its per-sample constants is (then every angle is NaN/inf): it is counted and
+            // contributes zeros to the per-angle sums; finite rows never produce a non-finite j_ion
+            const double probe = (bamp1[u] + bamp2[u] + j_cex[u]) * 0.0 + (bx1[u] + bx2[u]) * 0.0;
+            row_ok[u] = active[u] && (known_invalid ||   // alpha1 <= 0: the row is the finite 1e-20 fill whatever else is NaN
+                                      ((probe == 0.0) && !(bx1[u] == CUDART_INF) && !(bx2[u] == CUDART_INF)));
+            // plume.py:105-106: a sample with alpha1 <= 0 or any j_ion <= 0 has its whole row replaced by 1e-20.  Whether a
+            // non-positive j_ion exists must be known BEFORE the row is accumulated, so the (rare) samples that can have
+            // one -- negative amplitude or no CEX floor -- run a look-ahead sweep first.
+            invalid[u] = known_invalid;
+            if (!known_invalid && !(bamp1[u] >= 0.0 && bamp2[u] >= 0.0 && j_cex[u] > 0.0)) {
+                SweepBeam t1 = b1[u], t2 = b2[u];
+                bool any_bad = false;
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int i0 = c * kChunk;
+                    if (c != 0 && (c % kRestartChunks) == 0) {
+                        sweep_beam_restart(t1, bx1[u], i0);
+                        sweep_beam_restart(t2, bx2[u], i0);
+                    }
+                    double e1 = bamp1[u] * t1.ec, e2 = bamp2[u] * t2.ec, r1 = t1.rc, r2 = t2.rc;
+                    for (int kk = 0; kk < kChunk && i0 + kk < A; ++kk) {
+                        any_bad |= ((e1 + e2) + j_cex[u] <= 0.0);
+                        e1 *= r1; r1 *= t1.q;
+                        e2 *= r2; r2 *= t2.q;
+                    }
+                    sweep_beam_next(t1);
+                    sweep_beam_next(t2);
+                }
+                invalid[u] = any_bad;
+            }
+            if (!row_ok[u]) {   // non-finite (or inactive shadow) row: exact zeros to the per-angle sums, NaN to cos_div
+                b1[u].ec = b2[u].ec = 1.0;
+                b1[u].rc = b1[u].gc = b1[u].q = b1[u].qk = b1[u].hh = 1.0;
+                b2[u].rc = b2[u].gc = b2[u].q = b2[u].qk = b2[u].hh = 1.0;
+                bx1[u] = bx2[u] = 0.0;
+                bamp1[u] = bamp2[u] = 0.0;
+                j_cex[u] = 0.0;
+            }
+            j_fill[u] = row_ok[u] ? kInvalidFill : 0.0;
+        }
+        // warps whose 64 rows are all ordinary (finite, valid) -- virtually all of them -- skip the per-element selects
+        const bool plain = !__any_sync(0xffffffffu, invalid[0] || invalid[1] || !row_ok[0] || !row_ok[1]);
+        double2* my_row = tile + lane * kPairPitch;
+
+        auto sweep = [&](auto plain_tag) {
+            constexpr bool PLAIN = decltype(plain_tag)::value;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int i0 = c * kChunk;
+                if (RESTART && c != 0 && (c % kRestartChunks) == 0) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (row_ok[u]) {
+                            sweep_beam_restart(b1[u], bx1[u], i0);
+                            sweep_beam_restart(b2[u], bx2[u], i0);
+                        }
+                    }
+                }
+                double e1a = bamp1[0] * b1[0].ec, e2a = bamp2[0] * b2[0].ec, r1a = b1[0].rc, r2a = b2[0].rc;
+                double e1b = bamp1[1] * b1[1].ec, e2b = bamp2[1] * b2[1].ec, r1b = b1[1].rc, r2b = b2[1].rc;
+#pragma unroll
+                for (int kk = 0; kk < kChunk; ++kk) {
+                    const double2 w = wsm[i0 + kk];          // zero beyond A
+                    const double sa = e1a + e2a, sb = e1b + e2b;   // j_beam + j_scat
+                    den[0] = fma(w.x, sa, den[0]);
+                    num[0] = fma(w.y, sa, num[0]);
+                    den[1] = fma(w.x, sb, den[1]);
+                    num[1] = fma(w.y, sb, num[1]);
+                    double ja = sa + j_cex[0], jb = sb + j_cex[1];  // the values current_density() returns (plume.py:102)
+                    if (!PLAIN) {
+                        ja = invalid[0] ? j_fill[0] : ja;
+                        jb = invalid[1] ? j_fill[1] : jb;
+                    }
+                    my_row[kk] = make_double2(ja + jb, fma(jb, jb, ja * ja));   // columns >= A are never read back
+                    const bool is_hist = HS > 0 ? (kk % (HS > 0 ? HS : 1) == 0) : (HS < 0 && ((i0 + kk) & h_mask) == 0);
+                    if (HS != 0 && is_hist && i0 + kk < A) {
+                        unsigned* hrow = hist_blk + (size_t)((i0 + kk) >> m.hist_shift) * m.n_bins;
+                        hist_add(hrow, ja, PLAIN || row_ok[0], lane, h_shift, h_lo_key, h_last);
+                        hist_add(hrow, jb, PLAIN || row_ok[1], lane, h_shift, h_lo_key, h_last);
+                    }
+                    e1a *= r1a; r1a *= b1[0].q;
+                    e2a *= r2a; r2a *= b2[0].q;
+                    e1b *= r1b; r1b *= b1[1].q;
+                    e2b *= r2b; r2b *= b2[1].q;
+                }
+                sweep_beam_next(b1[0]); sweep_beam_next(b2[0]);
+                sweep_beam_next(b1[1]); sweep_beam_next(b2[1]);
+                __syncwarp();
+                // column sums over the warp's 64 samples: 2 lanes per angle, 16 rows each (two independent chains per sum)
+                {
+                    double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
+                    const double2* tcol = tile + (half * 16) * kPairPitch + col;
+#pragma unroll
+                    for (int rr = 0; rr < 16; rr += 2) {
+                        const double2 va = tcol[rr * kPairPitch], vb = tcol[(rr + 1) * kPairPitch];
+                        s1a += va.x; s1b += vb.x;
+                        s2a += va.y; s2b += vb.y;
+                    }
+                    double s1 = s1a + s1b, s2 = s2a + s2b;
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                    if (half == 0) {
+                        double2 a = acc[i0 + col];
+                        a.x += s1; a.y += s2;
+                        acc[i0 + col] = a;
+                    }
+                }
+                __syncwarp();
+            }
+        };
+        if (plain)
+            sweep(std::true_type{});
+        else
+            sweep(std::false_type{});
+
+        // ---- per-sample epilogue: plume.py:124-127,137 (NOT masked by `invalid`) ----
+        double cd[2], dv[2];
+        if (fast && __all_sync(0xffffffffu, fm_mid(den[0]) && fm_mid0(num[0]) && fm_mid(den[1]) && fm_mid0(num[1]))) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                cd[u] = fm_div(num[u], den[u]);
+                dv[u] = fm_acos(cd[u]);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                cd[u] = num[u] / den[u];
+                if (cd[u] == CUDART_INF) cd[u] = CUDART_NAN;  // plume.py:125
+                dv[u] = acos(cd[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (active[u]) {
+                c_samples += 1;
+                if (invalid[u]) c_invalid += 1;
+                if (!row_ok[u]) c_nonfinite += 1;
+                if (dv[u] == dv[u]) {
+                    const double d = dv[u] - m.shift[1];
+                    c_d += 1; s_d += d; q_d = fma(d, d, q_d);
+                    mm[2] = fmax(mm[2], -dv[u]); mm[3] = fmax(mm[3], dv[u]);
+                }
+                if (want_thrust) {
+                    const double tc = __dmul_rn(thrust[u], cd[u]);
+                    if (tc == tc) {
+                        const double d = tc - m.shift[2];
+                        c_t += 1; s_t += d; q_t = fma(d, d, q_t);
+                        mm[4] = fmax(mm[4], -tc); mm[5] = fmax(mm[5], tc);
+                    }
+                }
+            }
+        }
+    }
+    // ---- block reduction of the register accumulators, then one partial vector per block ----
+    // partial scalars: [0..2] counts, then per scalar {n, sum of (x - shift), sum of (x - shift)^2}
+    const double sc[kMomScalars] = {double(c_samples), double(c_invalid), double(c_nonfinite), double(c_v), s_v, q_v,
+                                    double(c_d), s_d, q_d, double(c_t), s_t, q_t};
+#pragma unroll
+    for (int i = 0; i < kMomScalars; ++i) {
+        double v = sc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double v = mm[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) red[warp][kMomScalars + i] = v;
+    }
+    __syncthreads();
+    const long long n_part = kMomScalars + 2LL * A;
+    double* out = m.partials + (long long)blockIdx.x * n_part;
+    if (threadIdx.x < kMomScalars) {
+        double v = 0.0;
+        for (int w = 0; w < n_warps; ++w) v += red[w][threadIdx.x];
+        out[threadIdx.x] = v;
+    } else if (threadIdx.x < kMomScalars + 6) {
+        double v = -CUDART_INF;
+        for (int w = 0; w < n_warps; ++w) v = fmax(v, red[w][threadIdx.x]);
+        m.partial_minmax[(long long)blockIdx.x * 6 + (threadIdx.x - kMomScalars)] = v;
+    }
+    for (int i = threadIdx.x; i < A; i += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int w = 0; w < n_warps; ++w) {
+            const double2 a = acc_all[w * a_pad + i];
+            s1 += a.x;
+            s2 += a.y;
+        }
+        out[kMomScalars + i] = s1;          // sum over the block's samples of j_ion[:, i]
+        out[kMomScalars + A + i] = s2;      // ... of j_ion[:, i]^2
+    }
+}
+
+// Chan / pairwise update of (n, S, M2) with another group (nb, Sb, M2b): M2 = sum of squared deviations from the mean
+__device__ __forceinline__ void chan_merge(double& n, double& S, double& M2, double nb, double Sb, double M2b) {
+    if (!(nb > 0.0)) return;
+    if (!(n > 0.0)) {
+        n = nb; S = Sb; M2 = M2b;
+        return;
+    }
+    const double delta = Sb / nb - S / n;
+    M2 += M2b + delta * delta * (n * nb / (n + nb));
+    S += Sb;
+    n += nb;
+}
+
+// Merge the per-block partial vectors (raw sums about the shifts) of ONE accumulate call into the caller's packed vector,
+// blocks in index order.  One thread per (scalar group | angle | histogram bin); the three counters [0..2] are read here
+// (the per-angle row count is sums[0] - sums[2]) and updated by moments_counts_kernel afterwards.
+__global__ void moments_finalize_kernel(const double* __restrict__ partials, const double* __restrict__ partial_minmax,
+                                        unsigned* __restrict__ hist_partials, int n_blocks, int n_angles, MomentsParams m,
+                                        double* __restrict__ sums, double* __restrict__ minmax) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n_part = kMomScalars + 2LL * n_angles;
+    if (i < 3) {
+        const int g = (int)i;   // V_cc, div_angle, T_c
+        double n = sums[3 + 3 * g], S = sums[4 + 3 * g], M2 = sums[5 + 3 * g];
+        for (int b = 0; b < n_blocks; ++b) {
+            const double* pb = partials + (long long)b * n_part + 3 + 3 * g;
+            const double nb = pb[0], Sd = pb[1], Qd = pb[2];
+            if (nb > 0.0) chan_merge(n, S, M2, nb, Sd + nb * m.shift[g], fmax(Qd - Sd * Sd / nb, 0.0));
+        }
+        sums[3 + 3 * g] = n; sums[4 + 3 * g] = S; sums[5 + 3 * g] = M2;
+    } else if (i >= m.off_angle_sum && i < m.off_angle_sum + n_angles) {
+        const int a = (int)(i - m.off_angle_sum);
+        double n = sums[0] - sums[2], S = sums[m.off_angle_sum + a], M2 = sums[m.off_angle_sumsq + a];
+        for (int b = 0; b < n_blocks; ++b) {
+            const double* pb = partials + (long long)b * n_part;
+            const double nb = pb[0] - pb[2], Sb = pb[kMomScalars + a], Qb = pb[kMomScalars + n_angles + a];
+            if (nb > 0.0) chan_merge(n, S, M2, nb, Sb, fmax(Qb - Sb * Sb / nb, 0.0));
+        }
+        sums[m.off_angle_sum + a] = S;
+        sums[m.off_angle_sumsq + a] = M2;
+    } else if (i >= m.off_hist && i < m.n_sums) {
+        const long long k = i - m.off_hist, per = (long long)m.n_hist_angles * m.n_bins;
+        unsigned long long v = 0;
+        for (int b = 0; b < n_blocks; ++b) {
+            v += hist_partials[(long long)b * per + k];
+            hist_partials[(long long)b * per + k] = 0u;
+        }
+        sums[i] += double(v);
+    }
+    if (i < 6 && minmax) {
+        double v = minmax[i];
+        for (int b = 0; b < n_blocks; ++b) v = fmax(v, partial_minmax[(long long)b * 6 + i]);
+        minmax[i] = v;
+    }
+}
+__global__ void moments_counts_kernel(const double* __restrict__ partials, int n_blocks, int n_angles, double* __restrict__ sums) {
+    const int i = threadIdx.x;
+    if (i < 3) {
+        const long long n_part = kMomScalars + 2LL * n_angles;
+        double v = 0.0;
+        for (int b = 0; b < n_blocks; ++b) v += partials[(long long)b * n_part + i];
+        sums[i] += v;
+    }
+}
+
+// Merge `n_parts` packed vectors (each [sums (n_sums) | minmax (6)], `stride` doubles apart) in index order into
+// out_sums / out_minmax (overwritten): what every rank runs after the all-gather, so all ranks hold the same bits
+// whatever order the collective moved the data in.
+__global__ void moments_merge_kernel(const double* __restrict__ parts, long long stride, int n_parts, int n_angles, MomentsParams m,
+                                     double* __restrict__ out_sums, double* __restrict__ out_minmax) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3) {   // counters
+        double v = 0.0;
+        for (int r = 0; r < n_parts; ++r) v += parts[r * stride + i];
+        out_sums[i] = v;
+        const int g = (int)i;
+        double n = 0.0, S = 0.0, M2 = 0.0;
+        for (int r = 0; r < n_parts; ++r) {
+            const double* pr = parts + r * stride + 3 + 3 * g;
+            chan_merge(n, S, M2, pr[0], pr[1], pr[2]);
+        }
+        out_sums[3 + 3 * g] = n; out_sums[4 + 3 * g] = S; out_sums[5 + 3 * g] = M2;
+    } else if (i >= m.off_angle_sum && i < m.off_angle_sum + n_angles) {
+        const int a = (int)(i - m.off_angle_sum);
+        double n = 0.0, S = 0.0, M2 = 0.0;
+        for (int r = 0; r < n_parts; ++r) {
+            const double* pr = parts + r * stride;
+            chan_merge(n, S, M2, pr[0] - pr[2], pr[m.off_angle_sum + a], pr[m.off_angle_sumsq + a]);
+        }
+        out_sums[m.off_angle_sum + a] = S;
+        out_sums[m.off_angle_sumsq + a] = M2;
+    } else if (i >= m.off_hist && i < m.n_sums) {
+        double v = 0.0;
+        for (int r = 0; r < n_parts; ++r) v += parts[r * stride + i];   // integer-valued, exact
+        out_sums[i] = v;
+    }
+    if (i < 6) {
+        double v = -CUDART_INF;
+        for (int r = 0; r < n_parts; ++r) v = fmax(v, parts[r * stride + m.n_sums + i]);
+        out_minmax[i] = v;
+    }
+}
+
+}  // namespace hpem

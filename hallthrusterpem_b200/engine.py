@@ -50,6 +50,22 @@ def _torch():
     return torch
 
 
+def resolve_devices(devices) -> list[int]:
+    """'all' -> every visible CUDA device; an int -> [int]; an iterable of ints -> list."""
+    torch = _torch()
+    if isinstance(devices, str):
+        if devices != 'all':
+            raise ValueError(f"devices must be 'all', an index or a list of indices, got {devices!r}")
+        devs = list(range(torch.cuda.device_count()))
+    elif isinstance(devices, int):
+        devs = [devices]
+    else:
+        devs = [int(d) for d in devices]
+    if not devs:
+        raise RuntimeError('hallthrusterpem_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    return devs
+
+
 def _is_torch_tensor(x: Any) -> bool:
     return type(x).__module__.startswith('torch') and hasattr(x, 'data_ptr')
 
@@ -103,7 +119,10 @@ def get_grid(device: int, n_angles: int, radii: np.ndarray) -> GridHandle:
         g = _grid_cache.get(key)
         if g is None:
             if len(_grid_cache) >= 64:
-                _grid_cache.pop(next(iter(_grid_cache))).close()
+                # evict the oldest entry from the cache only: callers that still hold the handle (PreparedCall, reducers,
+                # measurement sets, another thread inside hpem_eval_host) keep it alive; GridHandle.__del__ destroys it
+                # when the last of them lets go
+                _grid_cache.pop(next(iter(_grid_cache)))
             g = _grid_cache[key] = GridHandle(device, n_angles, radii)
         return g
 
@@ -160,10 +179,12 @@ class _Batch:
             size = 1
             for d in shape:
                 size *= int(d)
-            if size == 1:                                 # NumPy scalar broadcasting (test_plume.py:67-77)
+            if size == 1 and not (is_t and v.is_cuda):    # NumPy scalar broadcasting (test_plume.py:67-77)
                 struct.ptr[k] = None
                 struct.scalar[k] = float(v.reshape(-1)[0]) if shape != () or hasattr(v, 'reshape') else float(v)
                 continue
+            # (a one-element CUDA tensor stays a pointer, expanded to the loop shape: reading its value here would be a
+            #  blocking device->host copy, break CUDA-graph capture and bake a stale value into a cached PreparedCall)
             if self.on_device:
                 torch = _torch()
                 t = v if is_t else torch.as_tensor(np.asarray(v, dtype=np.float64))
@@ -238,14 +259,34 @@ def _alloc_host(shape: tuple[int, ...], dtype=np.float64) -> np.ndarray:
     return np.empty(shape, dtype=dtype)
 
 
+_pool = None
+_pool_lock = threading.Lock()
+
+
+def _thread_pool():
+    """Issuing threads of the single-process multi-GPU host path (ctypes releases the GIL inside the C call)."""
+    global _pool
+    with _pool_lock:
+        if _pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _pool = ThreadPoolExecutor(max_workers=16, thread_name_prefix='hpem-dev')
+        return _pool
+
+
 class PreparedCall:
     """One marshalled request: input struct, output buffers and grid handle.  `run()` issues the C-ABI call and may
-    be repeated (same buffers) -- bench.py times exactly this; `evaluate()` is prepare + run + results."""
+    be repeated (same buffers) -- bench.py times exactly this; `evaluate()` is prepare + run + results.
+
+    `device='all'` (or a list of indices) with HOST inputs shards the samples over several GPUs from this ONE process:
+    contiguous ranges cut at multiples of 64 samples (so every sample keeps its position modulo 4 / 32 and the outputs
+    are bit-identical to a single-GPU call), one `hpem_eval_host` pipeline per device, each writing its slice of the same
+    output arrays.  This is how the reference's actual caller -- amisc, one process, one call per batch
+    (pem_v0_SPT-100.yml:5-7,215-218) -- reaches all GPUs of the box."""
 
     def __init__(self, inputs: dict, *, want_cathode: bool, want_plume: bool, sweep_radius=1.0, n_angles: int = 91,
-                 torr: float | None = None, device: int | None = None, direct: bool = False,
+                 torr: float | None = None, device=None, direct: bool = False,
                  want_j_ion: bool = True, extras: bool = False, pin_outputs: bool = True, no_tma: bool = False,
-                 lanes1: bool = False, lanes4: bool = False, no_quad: bool = False):
+                 lanes1: bool = False, lanes4: bool = False, no_quad: bool = False, no_fastmath: bool = False):
         self.lib = _lib.load()
         names: tuple[str, ...] = ()
         if want_cathode:
@@ -269,12 +310,19 @@ class PreparedCall:
         torch = _torch()
         if not torch.cuda.is_available():
             raise RuntimeError('hallthrusterpem_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        devs = None
         if batch.on_device:
             dev = batch.device_index
+        elif device is None:
+            dev = torch.cuda.current_device()
+        elif isinstance(device, int):
+            dev = int(device)
         else:
-            dev = torch.cuda.current_device() if device is None else int(device)
+            devs = resolve_devices(device)
+            dev = devs[0]
         self.device = dev
-        self.grid = grid = get_grid(dev, n_angles, radii) if want_plume else get_grid(dev, 91, np.array([1.0]))
+        g_angles, g_radii = (n_angles, radii) if want_plume else (91, np.array([1.0]))
+        self.grid = grid = get_grid(dev, g_angles, g_radii)
 
         loop = batch.out_shape
         rshape = loop if single else loop + (n_radii,)
@@ -303,10 +351,29 @@ class PreparedCall:
                 result['cos_div'], out.cos_div = new(rshape)
                 result['invalid'], out.invalid = new(loop, np.uint8)
         self.flags = (_lib.FLAG_FORCE_DIRECT if direct else 0) | (_lib.FLAG_NO_TMA if no_tma else 0) \
-            | (_lib.FLAG_LANES1 if lanes1 else 0) | (_lib.FLAG_LANES4 if lanes4 else 0) | (_lib.FLAG_NO_QUAD if no_quad else 0)
+            | (_lib.FLAG_LANES1 if lanes1 else 0) | (_lib.FLAG_LANES4 if lanes4 else 0) | (_lib.FLAG_NO_QUAD if no_quad else 0) \
+            | (_lib.FLAG_NO_FASTMATH if no_fastmath else 0)
         self.h2d_bytes = 0 if batch.on_device else 8 * batch.n * sum(1 for k in range(_lib.N_INPUTS)
                                                                       if batch.struct.ptr[k])
         self.d2h_bytes = 0 if batch.on_device else sum(v.nbytes for v in result.values())
+        # single-process multi-GPU: per-device views of the same host buffers
+        self.shards = []
+        if devs is not None and len(devs) > 1 and batch.n >= 64 * len(devs):
+            from .synthetic import shard_bounds
+            row = grid.n_angles * n_radii
+            per_out = {'V_cc': 8, 'j_ion': 8 * row, 'div_angle': 8 * n_radii, 'T_c': 8 * n_radii, 'cos_div': 8 * n_radii, 'invalid': 1}
+            for r, d in enumerate(devs):
+                lo, hi = shard_bounds(batch.n, len(devs), r)
+                if hi <= lo:
+                    continue
+                si, so = _lib.HpemInputs(), _lib.HpemOutputs()
+                for k in range(_lib.N_INPUTS):
+                    si.ptr[k] = (batch.struct.ptr[k] + 8 * lo) if batch.struct.ptr[k] else None
+                    si.scalar[k] = batch.struct.scalar[k]
+                for name, stride in per_out.items():
+                    base = getattr(out, name)
+                    setattr(so, name, (base + stride * lo) if base else None)
+                self.shards.append((get_grid(d, g_angles, g_radii), hi - lo, si, so))
 
     def run(self, stream: int | None = None) -> None:
         """Device inputs: asynchronous launch on `stream` (default: torch's current stream).
@@ -320,6 +387,14 @@ class PreparedCall:
                 stream = torch.cuda.current_stream(self.device).cuda_stream
             _lib.check(self.lib.hpem_eval(self.grid.handle, b.n, ctypes.byref(b.struct), ctypes.byref(self.out),
                                           self.torr, self.flags, ctypes.c_void_p(stream)))
+        elif self.shards:
+            def one(shard):
+                g, count, si, so = shard
+                return self.lib.hpem_eval_host(g.handle, count, ctypes.byref(si), ctypes.byref(so), self.torr, self.flags), \
+                    self.lib.hpem_last_error().decode('utf-8', 'replace')      # thread-local text, read on the issuing thread
+            for status, msg in list(_thread_pool().map(one, self.shards)):
+                if status != _lib.HPEM_OK:
+                    raise _lib.HpemError(f'libhpem status {status}: {msg}')
         else:
             _lib.check(self.lib.hpem_eval_host(self.grid.handle, b.n, ctypes.byref(b.struct), ctypes.byref(self.out),
                                                self.torr, self.flags))

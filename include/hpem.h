@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HPEM_ABI_VERSION 1
+#define HPEM_ABI_VERSION 2
 
 /* status codes */
 #define HPEM_OK 0
@@ -96,9 +96,17 @@ typedef struct hpem_outputs {
 #define HPEM_FLAG_NO_QUAD 16u      /* angle counts that are not a multiple of 4: do not use K1u's quad-row tensor     \
                                      stores (diagnostics; falls back to (n, A) boxes / whole-row bulk stores) */
 
+#define HPEM_FLAG_NO_FASTMATH 32u  /* per-sample part (cathode, normalisations, CEX terms, recurrence start values, arccos)  \
+                                     through libdevice exp/log/acos and IEEE division even for warps whose samples are all \
+                                     in the nominal range (default: the branch-free functions of csrc/hpem_fastmath.cuh;   \
+                                     both back ends meet the rel-1e-12 parity rule, they differ in last bits) */
+
 typedef struct hpem_grid hpem_grid; /* opaque */
 
 int hpem_abi_version(void);
+/* 16 hex digits: hash of the sources this binary was compiled from (the Python loader refuses a binary that does not
+ * belong to its source tree, whatever the file's mtime says). */
+const char *hpem_source_hash(void);
 /* Thread-local text of the last error raised on the calling thread ("" if none). */
 const char *hpem_last_error(void);
 
@@ -131,15 +139,18 @@ int hpem_eval_host(hpem_grid *grid, int64_t n, const hpem_inputs *in, const hpem
  *
  * sums buffer (float64, length layout.n_sums; counts are stored as float64 so ONE ncclSum all-reduce merges ranks):
  *   [0] n_samples  [1] n_invalid (plume.py:105)  [2] n_nonfinite_rows (NaN/inf samples, excluded from angle sums)
- *   [3..5] V_cc: n_finite, sum, sum of squares   [6..8] div_angle: same   [9..11] T_c: same
+ *   [3..5] V_cc: n_finite, sum, M2 = sum of squared deviations from the mean   [6..8] div_angle: same   [9..11] T_c: same
  *   [off_angle_sum + i]   sum over samples of j_ion[:, i]      (values exactly as current_density() returns them,
- *   [off_angle_sumsq + i] sum over samples of j_ion[:, i]^2     i.e. 1e-20 for invalid samples)
+ *   [off_angle_sumsq + i] M2 of j_ion[:, i] over those samples  i.e. 1e-20 for invalid samples; n = [0] - [2])
+ *        Second moments are CENTRED and merged pairwise (Chan et al.) block by block, call by call and rank by rank, so a
+ *        variance M2/n never comes from E[x^2] - E[x]^2 over the population.  A packed vector is therefore NOT additive:
+ *        merge vectors with hpem_moments_merge (or the same update on the host), not with a plain sum.
  *   [off_hist + a*n_bins + b] histogram count of j_ion[:, a*hist_angle_stride] in bin b:
  *        bin 0: j < 2^hist_min_exp2 (incl. <= 0);  bin n_bins-1: j >= 2^hist_max_exp2;  otherwise log-linear:
  *        b = 1 + floor((log2-octave - hist_min_exp2) * 2^hist_sub_bits + linear sub-bin within the octave)
- * minmax buffer (float64, length 6): (-min, max) of V_cc, div_angle, T_c -> merge ranks with ONE ncclMax all-reduce.
+ * minmax buffer (float64, length 6): (-min, max) of V_cc, div_angle, T_c.
  * Both buffers are ACCUMULATED into (call hpem_moments_accumulate once per chunk of samples); initialise sums to 0
- * and minmax to -inf. */
+ * and minmax to -inf.  Ranks: all-gather the [sums | minmax] vectors (ONE collective), then hpem_moments_merge. */
 typedef struct hpem_moments_spec {
     int32_t hist_angle_stride; /* power of two; histogram every stride-th angle; 0 = no histograms */
     int32_t hist_sub_bits;     /* 2^sub_bits bins per octave, 0..6 */
@@ -147,6 +158,9 @@ typedef struct hpem_moments_spec {
     int32_t hist_max_exp2;     /* one past the last octave */
     int32_t want_cathode;      /* accumulate V_cc moments (reads the six cathode inputs) */
     int32_t want_thrust;       /* accumulate T_c moments (reads input T) */
+    double scalar_shift[3];    /* V_cc, div_angle, T_c are accumulated about these values inside the kernel (any finite
+                                  number near the expected mean; 0 is fine).  The packed vector does not depend on them
+                                  beyond rounding. */
 } hpem_moments_spec;
 
 typedef struct hpem_moments_layout {
@@ -164,6 +178,12 @@ int hpem_moments_layout_query(const hpem_grid *grid, const hpem_moments_spec *sp
 /* DEVICE buffers, asynchronous on `stream`.  `sums` (layout.n_sums doubles) and `minmax` (6 doubles) are updated. */
 int hpem_moments_accumulate(hpem_grid *grid, int64_t n, const hpem_inputs *in, double torr_2_pa,
                             const hpem_moments_spec *spec, double *sums, double *minmax, void *stream);
+
+/* Merge n_parts packed vectors, part r = [sums (layout.n_sums) | minmax (6)] at parts + r * part_stride (DEVICE memory),
+ * in index order into sums / minmax (DEVICE, overwritten; must not alias parts).  Every rank runs this on the all-gathered
+ * buffer, so all ranks end up with identical bits whatever order the collective moved the data in. */
+int hpem_moments_merge(int device, const hpem_moments_layout *layout, int n_parts, const double *parts, int64_t part_stride,
+                       double *sums, double *minmax, void *stream);
 
 /* ---- on-device sampler for the input priors (the step before the path: amisc `sample_inputs`, gen_data.py:238) ----
  * Counter-based (Philox4x32-10): the inputs of global sample index i depend only on (seed, i), never on the shard,

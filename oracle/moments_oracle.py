@@ -33,13 +33,14 @@ def packed_moments(layout, j_ion, v_cc, div_angle, t_c, invalid):
         ok = ~np.isnan(x)
         sums[3 + 3 * k] = ok.sum()
         sums[4 + 3 * k] = x[ok].sum()
-        sums[5 + 3 * k] = (x[ok] ** 2).sum()
+        sums[5 + 3 * k] = ((x[ok] - x[ok].mean()) ** 2).sum() if ok.any() else 0.0     # M2: centred (include/hpem.h)
         if ok.any():
             minmax[2 * k] = -x[ok].min()
             minmax[2 * k + 1] = x[ok].max()
     jj = j_ion[row_ok]
     sums[layout.off_angle_sum:layout.off_angle_sum + A] = jj.sum(axis=0)
-    sums[layout.off_angle_sumsq:layout.off_angle_sumsq + A] = (jj ** 2).sum(axis=0)
+    if jj.shape[0]:
+        sums[layout.off_angle_sumsq:layout.off_angle_sumsq + A] = ((jj - jj.mean(axis=0)) ** 2).sum(axis=0)
     sp = layout.spec
     if sp.angle_stride > 0:
         h = np.zeros((layout.n_hist_angles, layout.n_bins))

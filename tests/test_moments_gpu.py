@@ -33,17 +33,23 @@ def test_moments_match_materialised_path(n, n_angles, chunks, cuda_device):
     L = mc.layout
     assert np.array_equal(res.sums[:3], sums[:3])
     assert np.array_equal(res.sums[[3, 6, 9]], sums[[3, 6, 9]])
-    np.testing.assert_allclose(res.sums[3:12], sums[3:12], rtol=1e-12)
-    np.testing.assert_allclose(res.sums[L.off_angle_sum:L.off_hist], sums[L.off_angle_sum:L.off_hist], rtol=1e-12)
+    # sums to rel 1e-12; centred second moments (Chan merges on the device, two-pass NumPy here) to 1e-11
+    np.testing.assert_allclose(res.sums[[4, 7, 10]], sums[[4, 7, 10]], rtol=1e-12)
+    np.testing.assert_allclose(res.sums[[5, 8, 11]], sums[[5, 8, 11]], rtol=1e-11)
+    np.testing.assert_allclose(res.sums[L.off_angle_sum:L.off_angle_sumsq], sums[L.off_angle_sum:L.off_angle_sumsq], rtol=1e-12)
+    np.testing.assert_allclose(res.sums[L.off_angle_sumsq:L.off_hist], sums[L.off_angle_sumsq:L.off_hist], rtol=1e-11)
     assert np.array_equal(res.sums[L.off_hist:], sums[L.off_hist:]), 'histogram counts differ'
     np.testing.assert_allclose(res.minmax, minmax, rtol=1e-13)
     assert res.histograms.sum(axis=1).tolist() == [n] * L.n_hist_angles
     # decoded statistics against NumPy on the materialised arrays
     np.testing.assert_allclose(res.j_mean, out['j_ion'].mean(axis=0), rtol=1e-12)
     assert abs(res.scalar('div_angle')['mean'] - out['div_angle'].mean()) < 1e-12
-    p50 = res.j_percentile(50)[0]
-    ref50 = np.percentile(out['j_ion'][:, L.hist_angle_index], 50, axis=0)
-    assert np.all(np.abs(p50 / ref50 - 1) < 0.15)          # 8 bins per octave -> <= 12.5 % bin width
+    np.testing.assert_allclose(res.j_var, out['j_ion'].var(axis=0), rtol=1e-11)
+    assert abs(res.scalar('V_cc')['var'] - out['V_cc'].var()) < 1e-11 * out['V_cc'].var()
+    # the percentiles the reference's consumers take (tests/test_plume.py:50-52), interpolated inside the 8-per-octave bins
+    pq = res.j_percentile([5, 50, 95])
+    ref = np.percentile(out['j_ion'][:, L.hist_angle_index], [5, 50, 95], axis=0)
+    assert np.all(np.abs(pq / ref - 1) < (0.02 if n >= 5000 else 0.12)), np.abs(pq / ref - 1).max()
 
 
 def test_moments_against_oracle_with_edge_cases(cuda_device):
@@ -65,8 +71,8 @@ def test_moments_against_oracle_with_edge_cases(cuda_device):
     L = mc.layout
     assert np.array_equal(res.sums[:3], sums[:3]), (res.sums[:3], sums[:3])
     assert np.array_equal(res.sums[[3, 6, 9]], sums[[3, 6, 9]])
-    np.testing.assert_allclose(res.sums[3:12], sums[3:12], rtol=1e-11)
-    np.testing.assert_allclose(res.sums[L.off_angle_sum:L.off_hist], sums[L.off_angle_sum:L.off_hist], rtol=1e-11)
+    np.testing.assert_allclose(res.sums[3:12], sums[3:12], rtol=1e-10)
+    np.testing.assert_allclose(res.sums[L.off_angle_sum:L.off_hist], sums[L.off_angle_sum:L.off_hist], rtol=1e-10)
     # histogram counts may differ from the oracle only where a value sits within rounding of a bin edge
     diff = np.abs(res.sums[L.off_hist:] - sums[L.off_hist:]).sum()
     assert diff <= 2 * 4, diff
@@ -81,3 +87,49 @@ def test_moments_without_histograms_and_thrust(cuda_device):
     res = mc.result()
     assert res.n_samples == 1000 and res.layout.n_sums == 12 + 2 * 91
     assert res.scalar('T_c')['n'] == 0 and res.scalar('V_cc')['n'] == 1000
+
+
+def test_merge_kernel_matches_host_merge_and_sharded_sampling_is_exact(cuda_device):
+    """(i) hpem_moments_merge == the NumPy statement of the same pairwise update; (ii) four shards of one sampled index
+    range merged == the unsharded pass: counts and histograms bit for bit (index-addressed sampler), sums to 1e-12."""
+    import torch
+    from hallthrusterpem_b200.mc import HistogramSpec, MonteCarloMoments, merge_packed, merge_packed_host
+    from hallthrusterpem_b200.synthetic import shard_bounds
+    n, A, seed = 300_000, 91, 11
+    whole = MonteCarloMoments(n_angles=A, hist=HistogramSpec(), device=0, torr=133.322)
+    whole.accumulate_sampled(n, seed, 1000)
+    parts = []
+    for r in range(4):
+        lo, hi = shard_bounds(n, 4, r)
+        m = MonteCarloMoments(n_angles=A, hist=HistogramSpec(), device=0, torr=133.322)
+        m.accumulate_sampled(hi - lo, seed, 1000 + lo)
+        parts.append(m.packed.clone())
+    parts = torch.stack(parts)
+    merged = merge_packed(whole.layout, parts).cpu().numpy()
+    host = merge_packed_host(whole.layout, parts.cpu().numpy())
+    L = whole.layout
+    np.testing.assert_allclose(merged[:L.n_sums], host[:L.n_sums], rtol=1e-14)
+    assert np.array_equal(merged[L.n_sums:], host[L.n_sums:])
+    ref = whole.packed.cpu().numpy()
+    assert np.array_equal(merged[:3], ref[:3]) and np.array_equal(merged[[3, 6, 9]], ref[[3, 6, 9]])
+    assert np.array_equal(merged[L.off_hist:L.n_sums], ref[L.off_hist:L.n_sums]), 'histograms differ between shardings'
+    assert np.array_equal(merged[L.n_sums:], ref[L.n_sums:])
+    np.testing.assert_allclose(merged[:L.off_hist], ref[:L.off_hist], rtol=1e-12)
+
+
+def test_multi_device_reducer_matches_single_device(cuda_device):
+    """MonteCarloMoments(devices='all'): one process, the index range split over every visible GPU, merged on the first."""
+    import torch
+    from hallthrusterpem_b200.mc import HistogramSpec, MonteCarloMoments
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs >= 2 GPUs')
+    n, A = 400_000, 200
+    one = MonteCarloMoments(n_angles=A, hist=HistogramSpec(), device=0, torr=133.322)
+    one.accumulate_sampled(n, 5, 0)
+    many = MonteCarloMoments(n_angles=A, hist=HistogramSpec(), devices='all', torr=133.322)
+    many.accumulate_sampled(n, 5, 0)
+    a, b = one.result(), many.result()
+    L = one.layout
+    assert np.array_equal(a.sums[:3], b.sums[:3]) and np.array_equal(a.sums[L.off_hist:], b.sums[L.off_hist:])
+    np.testing.assert_allclose(a.sums[:L.off_hist], b.sums[:L.off_hist], rtol=1e-12)
+    assert np.array_equal(a.minmax, b.minmax)
