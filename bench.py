@@ -185,9 +185,9 @@ class ClockSampler:
         time.sleep(0.1)
         self.proc.terminate()
         rows = [r for t, r in self.rows if t0 <= t <= t1]
-        window = 'busy window around the timed steps'
+        window = 'the timed steps and the ~0.6 s back-to-back loop of the same kernel that follows them'
         if not rows:
-            rows, window = [r for _, r in self.rows], 'whole run (no sample fell inside the busy window)'
+            rows, window = [r for _, r in self.rows], 'whole run (no sample fell inside the window)'
         sm, smax, reasons = [], None, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in rows:
@@ -216,7 +216,7 @@ def _max_over_ranks(x: float, dev, world):
     return float(t.item())
 
 
-def bench_mc(name, n_total, n_angles, scaling, rank, world, dev, local_rank, barrier, fp64_peak, chunk=4_000_000):
+def bench_mc(name, n_total, n_angles, scaling, rank, world, dev, local_rank, barrier, fp64_peak, chunk=25_000_000):
     """Reduce-only Monte-Carlo (BASELINE configs 4 / 5): every rank accumulates its contiguous shard of ONE global sample index
     range (inputs drawn on the device), then ONE all-gather + fixed-order merge; both inside the CUDA-event region."""
     import torch
@@ -461,35 +461,43 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def busy(seconds):                      # keep the GPU on the same kernel so the clock samples bracket the timed steps
-        t_end = time.perf_counter() + seconds
-        while time.perf_counter() < t_end:
-            for _ in range(50):
-                call.run()
-            torch.cuda.synchronize()
-
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         call.run()
     barrier()
-    t_busy0 = time.perf_counter()
-    busy(0.4)
     launches0 = lib.hpem_launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    t_steps0 = time.perf_counter()
     evs[0].record(stream)
     for s in range(args.steps):
         call.run()
         evs[s + 1].record(stream)
     barrier()
+    t_steps1 = time.perf_counter()
     launches = lib.hpem_launch_count() - launches0
-    busy(0.4)
-    t_busy1 = time.perf_counter()
-    clocks = sampler.stop(t_busy0, t_busy1) if sampler else None
     total_ms = evs[0].elapsed_time(evs[-1])
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     total_ms_max = _max_over_ranks(total_ms, dev, world)
     value = world * n * A * args.steps / (total_ms_max * 1e-3)
+
+    # The K timed steps last a few milliseconds -- shorter than one nvidia-smi sample.  Directly after them the SAME kernel
+    # runs back to back for ~0.6 s, timed the same way: the clocks are sampled over steps + loop, and the loop gives the
+    # sustained rate (on this part the 1000 W cap pulls the SM clock down within ~0.2 s of continuous fp64 + HBM work;
+    # `value` is what one batch -- or a few -- gets, `sustained` what a long stream of batches gets).
+    sus_n = max(200, int(0.6 / max(total_ms / args.steps * 1e-3, 1e-5)))
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es0.record(stream)
+    for _ in range(sus_n):
+        call.run()
+    es1.record(stream)
+    barrier()
+    t_sus1 = time.perf_counter()
+    sus_ms = _max_over_ranks(es0.elapsed_time(es1), dev, world)
+    clocks = sampler.stop(t_steps0, t_sus1) if sampler else None
+    sustained = {'value': world * n * A * sus_n / (sus_ms * 1e-3), 'unit': UNIT, 'steps': sus_n, 'ms_per_step': sus_ms / sus_n,
+                 'hbm_gbs': ALG_BYTES_PER_EVAL * n * A / (sus_ms / sus_n * 1e-3) / 1e9,
+                 'note': 'same kernel, same buffers, back to back for ~0.6 s right after the timed steps'}
 
     # ---- e2e: public API, host buffers (pinned inputs), H2D + D2H inside the timed region, every rank ----
     from hallthrusterpem_b200.models import plume_cathode
@@ -521,6 +529,7 @@ def run_ours(args):
     fp_path = ROOT / 'profiles' / 'fp64_peak.json'
     if fp_path.exists():
         fp64_peak = json.loads(fp_path.read_text()).get('dfma_per_s_sustained')
+    sustained['hbm_frac'] = sustained['hbm_gbs'] / peak
 
     # ---- the reduce-only Monte-Carlo path with its collective (BASELINE configs 4 and 5), and config 3 at full size ----
     mc_blocks, cfg3 = None, None
@@ -554,6 +563,7 @@ def run_ours(args):
                              'frac_of_dfma_peak': 11.0 * n * A / (kernel_ms * 1e-3) / fp64_peak,
                              'note': 'non-binding axis: the recurrence kernel executes ~11 fp64-pipe instructions per evaluation '
                                      '(direct evaluation with two exp() per evaluation would need ~41)'}},
+            'sustained': sustained,
             'cpu_baseline': cpu_base,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': e2e_steps, 'inputs': 'pinned',

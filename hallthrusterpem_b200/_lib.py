@@ -112,7 +112,11 @@ def embedded_hash(path: Path) -> str | None:
 
 def nvcc_command(out: Path = LIB_PATH) -> list[str]:
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
-    return [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+    # -fmad=false: every fused multiply-add in the kernels is written as fma(); the compiler never contracts a * b + c on
+    # its own, so one expression gives the same bits in every kernel and template instantiation it is inlined into
+    # (K2 from arrays == K2 with on-device sampling == K1u, bit for bit) and the reference's separately-rounded
+    # multiply-adds stay separately rounded.  Measured cost: none (the hot loops are explicit fma / mul / add already).
+    return [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-fmad=false',
             f'-DHPEM_SOURCE_HASH={source_hash()}', '-Xcompiler', '-fPIC', '-shared', '-o', str(out), str(CSRC / 'hpem_api.cu')]
 
 

@@ -935,6 +935,7 @@ int hpem_moments_merge(int device, const hpem_moments_layout* lay, int n_parts, 
 
 static int fill_sampler(uint64_t seed, uint64_t first_index, const hpem_prior* priors, hpem::SamplerParams* sp) {
     if (!priors) return fail(HPEM_ERR_INVALID_ARG, "priors must be non-NULL");
+    sp->log_mask = sp->normal_mask = 0u;
     for (int k = 0; k < HPEM_N_INPUTS; ++k) {
         const hpem_prior& q = priors[k];
         if (q.kind < HPEM_PRIOR_CONST || q.kind > HPEM_PRIOR_NORMAL) return fail(HPEM_ERR_INVALID_ARG, "prior %d: unknown kind %d", k, q.kind);
@@ -946,6 +947,11 @@ static int fill_sampler(uint64_t seed, uint64_t first_index, const hpem_prior* p
         // LogUniform: exp(u (ln b - ln a) + ln a); the two logarithms are per-prior constants, taken once here
         sp->prior[k].log_a = q.kind == HPEM_PRIOR_LOGUNIFORM ? std::log(q.a) : 0.0;
         sp->prior[k].log_ratio = q.kind == HPEM_PRIOR_LOGUNIFORM ? std::log(q.b) - std::log(q.a) : 0.0;
+        // value = scale * u + offset (then exp for LogUniform; Normal is drawn separately)
+        sp->scale[k] = q.kind == HPEM_PRIOR_UNIFORM ? q.b - q.a : q.kind == HPEM_PRIOR_LOGUNIFORM ? sp->prior[k].log_ratio : 0.0;
+        sp->offset[k] = q.kind == HPEM_PRIOR_LOGUNIFORM ? sp->prior[k].log_a : q.a;
+        if (q.kind == HPEM_PRIOR_LOGUNIFORM) sp->log_mask |= 1u << k;
+        if (q.kind == HPEM_PRIOR_NORMAL) sp->normal_mask |= 1u << k;
     }
     sp->seed = seed;
     sp->first_index = first_index;

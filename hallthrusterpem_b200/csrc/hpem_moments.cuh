@@ -10,7 +10,7 @@
 // chains.  The per-angle sums over samples need a transposition (thread = sample for the sweep and the quadrature,
 // thread = angle for the column sums).  The two samples of a thread are combined in registers first,
 //        t = jA + jB,   q = jA^2 + jB^2,
-// so the 32 x 16 tile that goes through shared memory holds one (t, q) pair per TWO evaluations: 16-byte conflict-free
+// so the tile that goes through shared memory holds one (t, q) pair per TWO evaluations: 16-byte conflict-free
 // stores, 16-byte column loads, half the shared-memory traffic of a value-per-evaluation tile (the first version was as
 // busy on the shared-memory pipe as on the fp64 pipe).  Column sums: 2 lanes per angle, 16 rows each, added into
 // per-warp accumulators; one partial vector per block at the end, merged in block order by moments_finalize_kernel
@@ -47,13 +47,17 @@ constexpr int kMomScalars = 12;  // n_samples n_invalid n_nonfinite_rows | {n_fi
 #ifndef HPEM_THREADS_M
 #define HPEM_THREADS_M 384
 #endif
+#ifndef HPEM_HIST_LAG
+#define HPEM_HIST_LAG 5          // recurrence steps between a histogram MATCH and the use of its result
+#endif
 constexpr int kThreadsM = HPEM_THREADS_M;   // upper bound; the launch picks the warp count that fits shared memory
 constexpr int kMaxWarpsM = kThreadsM / 32;
-constexpr int kPairPitch = 17;              // double2 per tile row: odd -> conflict-free 16-byte stores and column loads
+constexpr int kHalfPitch = 9;               // double2 per half-tile row (8 angles + 1): odd -> conflict-free 16-byte stores and column loads
+constexpr int kTileElems = 2 * 32 * kHalfPitch;   // double2 per warp: two half-tiles of 32 rows
 
 // shared memory of one block with `warps` warps: fused weights + per-warp (t, q) tile + per-warp per-angle accumulators
 __host__ __device__ inline size_t moments_smem_bytes(int n_angles_pad, int a_pad, int warps) {
-    return size_t(n_angles_pad) * sizeof(double2) + size_t(warps) * 32 * kPairPitch * sizeof(double2) +
+    return size_t(n_angles_pad) * sizeof(double2) + size_t(warps) * kTileElems * sizeof(double2) +
            size_t(warps) * a_pad * sizeof(double2);
 }
 
@@ -85,13 +89,17 @@ __device__ __forceinline__ void sweep_beam_next(SweepBeam& b) {
     b.rc *= b.qk;
 }
 
-// one histogram update of the warp: lanes with the same bin elect their lowest lane, which adds the group size
-__device__ __forceinline__ void hist_add(unsigned* hrow, double j, bool ok, int lane, int h_shift, int h_lo_key, int h_last) {
-    // log-linear bin: octave from the exponent field, 2^sub_bits linear sub-bins from the leading mantissa bits.
+// Histogram update of the warp in two halves, so that the latency of MATCH (the slowest instruction of the sweep) is covered
+// by the recurrence steps between them.  hist_bin_match: log-linear bin of j and the mask of lanes in the same bin;
+// hist_commit: the lowest lane of every group adds the group size to the block's histogram row (one reduction per bin).
+__device__ __forceinline__ unsigned hist_bin_match(double j, bool ok, int h_shift, int h_lo_key, int h_last, int& b) {
+    // octave from the exponent field, 2^sub_bits linear sub-bins from the leading mantissa bits.
     // bin 0 = underflow (incl. zero/negative: the shifted pattern is negative), last bin = overflow (incl. +inf)
-    const int b = min(max((__double2hiint(j) >> h_shift) - h_lo_key, 0), h_last);
-    const unsigned peers = __match_any_sync(0xffffffffu, ok ? b : -1);
-    if (ok && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(hrow + b, (unsigned)__popc(peers));
+    b = min(max((__double2hiint(j) >> h_shift) - h_lo_key, 0), h_last);
+    return ok ? __match_any_sync(0xffffffffu, b) & ~0u : (__match_any_sync(0xffffffffu, -1), 0u);
+}
+__device__ __forceinline__ void hist_commit(unsigned* hrow, int b, unsigned peers, unsigned lanemask_lt) {
+    if (peers != 0u && (peers & lanemask_lt) == 0u) atomicAdd(hrow + b, (unsigned)__popc(peers));
 }
 
 // HS: histogram angle stride known at compile time (8, the default), 0 = no histograms, -1 = any power-of-two stride.
@@ -105,12 +113,12 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
     const int a_pad = n_chunks * kChunk;
     const int n_warps = blockDim.x >> 5;
     double2* wsm = reinterpret_cast<double2*>(smem_m);                      // [n_angles_pad]
-    double2* tiles = wsm + p.n_angles_pad;                                  // [warps][32][kPairPitch]
-    double2* acc_all = tiles + n_warps * 32 * kPairPitch;                   // [warps][a_pad]
+    double2* tiles = wsm + p.n_angles_pad;                                  // [warps][2][32][kHalfPitch]
+    double2* acc_all = tiles + n_warps * kTileElems;                        // [warps][a_pad]
     __shared__ double red[kMaxWarpsM][kMomScalars + 6];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double2* tile = tiles + warp * 32 * kPairPitch;
+    double2* tile = tiles + warp * kTileElems;
     double2* acc = acc_all + warp * a_pad;
     for (int i = threadIdx.x; i < p.n_angles_pad; i += blockDim.x) wsm[i] = p.w[i];
     for (int i = threadIdx.x; i < n_warps * a_pad; i += blockDim.x) acc_all[i] = make_double2(0.0, 0.0);
@@ -122,11 +130,11 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
     double mm[6] = {-CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF};
     const bool want_cathode = m.want_cathode != 0;
     const bool want_thrust = p.has_thrust;
-    const int col = lane & (kChunk - 1), half = lane >> 4;
     const int h_shift = 20 - m.hist_sub_bits, h_last = m.n_bins - 1;
     const int h_lo_key = ((m.hist_min_exp2 + 1023) << m.hist_sub_bits) - 1;
     const int h_mask = max(m.hist_stride, 1) - 1;
     unsigned* hist_blk = m.hist_partials + (size_t)blockIdx.x * m.n_hist_angles * m.n_bins;
+    const unsigned lanemask_lt = (1u << lane) - 1u;
 
     const long long batch = (long long)n_warps * 64;
     for (long long b0 = (long long)blockIdx.x * batch; b0 < p.n; b0 += (long long)gridDim.x * batch) {
@@ -136,18 +144,22 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
         // ---- the two samples of this thread: inputs ----
         double x_in[2][kNumInputs];
         bool active[2];
+        unsigned long long sidx[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const long long s_raw = w0 + u * 32 + lane;
             active[u] = s_raw < p.n;
-            const long long s = active[u] ? s_raw : p.n - 1;   // inactive lanes shadow the last sample, contribute nothing
-            if (SAMPLED) {
-                sample_inputs(sp, (unsigned long long)s, x_in[u]);
-            } else {
+            sidx[u] = (unsigned long long)(active[u] ? s_raw : p.n - 1);   // inactive lanes shadow the last sample, contribute nothing
+        }
+        if (SAMPLED) {
+            sample_inputs_n<2>(sp, sidx, x_in);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
 #pragma unroll
                 for (int q = 0; q < kNumInputs; ++q) {
                     const bool needed = (q == IN_P_b) || (q <= IN_P_T ? want_cathode : (q == IN_T ? want_thrust : true));
-                    x_in[u][q] = needed ? load_in(p, q, s) : 0.0;
+                    x_in[u][q] = needed ? load_in(p, q, (long long)sidx[u]) : 0.0;
                 }
             }
         }
@@ -236,10 +248,35 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
         }
         // warps whose 64 rows are all ordinary (finite, valid) -- virtually all of them -- skip the per-element selects
         const bool plain = !__any_sync(0xffffffffu, invalid[0] || invalid[1] || !row_ok[0] || !row_ok[1]);
-        double2* my_row = tile + lane * kPairPitch;
+        // The 16-angle chunk goes through shared memory as two half-tiles of 8 angles, [32 rows][kHalfPitch] (t, q) pairs each.
+        // While a thread sweeps one half it column-reduces the OTHER one, one row per recurrence step, so the loads and
+        // additions of the reduction are scheduled inside the fp64 stream of the sweep instead of forming a latency-bound
+        // phase of their own between two warp barriers.  Lane (c8 = lane & 7, q4 = lane >> 3) sums column c8 over rows 8 q4 .. 8 q4 + 7.
+        double2* my0 = tile + lane * kHalfPitch;                        // this thread's row in half-tile 0 (angles 0-7 of a chunk)
+        double2* my1 = my0 + 32 * kHalfPitch;                           // ... in half-tile 1 (angles 8-15)
+        const int c8 = lane & 7, q4 = lane >> 3;
+        const double2* col0 = tile + (q4 * 8) * kHalfPitch + c8;
+        const double2* col1 = col0 + 32 * kHalfPitch;
 
         auto sweep = [&](auto plain_tag) {
             constexpr bool PLAIN = decltype(plain_tag)::value;
+            unsigned* hrow = hist_blk;                       // histogram row of the next histogrammed angle
+            unsigned pend_pa = 0u, pend_pb = 0u;             // pending (matched, not yet committed) histogram update
+            int pend_ba = 0, pend_bb = 0;
+            double ra1 = 0.0, rb1 = 0.0, ra2 = 0.0, rb2 = 0.0;   // running column sums of the half-tile being reduced (two chains each)
+            auto finish_half = [&](int angle_base, bool keep) {
+                double s1 = ra1 + rb1, s2 = ra2 + rb2;
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                if (keep && q4 == 0) {
+                    double2 a = acc[angle_base + c8];
+                    a.x += s1; a.y += s2;
+                    acc[angle_base + c8] = a;
+                }
+                ra1 = rb1 = ra2 = rb2 = 0.0;
+            };
             for (int c = 0; c < n_chunks; ++c) {
                 const int i0 = c * kChunk;
                 if (RESTART && c != 0 && (c % kRestartChunks) == 0) {
@@ -266,42 +303,53 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
                         ja = invalid[0] ? j_fill[0] : ja;
                         jb = invalid[1] ? j_fill[1] : jb;
                     }
-                    my_row[kk] = make_double2(ja + jb, fma(jb, jb, ja * ja));   // columns >= A are never read back
-                    const bool is_hist = HS > 0 ? (kk % (HS > 0 ? HS : 1) == 0) : (HS < 0 && ((i0 + kk) & h_mask) == 0);
-                    if (HS != 0 && is_hist && i0 + kk < A) {
-                        unsigned* hrow = hist_blk + (size_t)((i0 + kk) >> m.hist_shift) * m.n_bins;
-                        hist_add(hrow, ja, PLAIN || row_ok[0], lane, h_shift, h_lo_key, h_last);
-                        hist_add(hrow, jb, PLAIN || row_ok[1], lane, h_shift, h_lo_key, h_last);
+                    (kk < 8 ? my0 : my1)[kk & 7] = make_double2(ja + jb, fma(jb, jb, ja * ja));   // columns >= A are never read back
+                    {   // one row of the other half-tile (chunk c-1's angles 8-15 during steps 0-7, this chunk's 0-7 during 8-15)
+                        const double2 v = (kk < 8 ? col1 : col0)[(kk & 7) * kHalfPitch];
+                        if (kk & 1) { rb1 += v.x; rb2 += v.y; } else { ra1 += v.x; ra2 += v.y; }
+                    }
+                    if (HS > 0) {          // compile-time stride: match at the histogrammed angle, commit a few steps later
+                        constexpr int kLag = (HS > HPEM_HIST_LAG ? HPEM_HIST_LAG : HS - 1);
+                        if (kk % (HS > 0 ? HS : 1) == 0 && i0 + kk < A) {
+                            pend_pa = hist_bin_match(ja, PLAIN || row_ok[0], h_shift, h_lo_key, h_last, pend_ba);
+                            pend_pb = hist_bin_match(jb, PLAIN || row_ok[1], h_shift, h_lo_key, h_last, pend_bb);
+                        }
+                        if (kk % (HS > 0 ? HS : 1) == kLag && i0 + kk - kLag < A) {
+                            hist_commit(hrow, pend_ba, pend_pa, lanemask_lt);
+                            hist_commit(hrow, pend_bb, pend_pb, lanemask_lt);
+                            hrow += m.n_bins;
+                        }
+                    } else if (HS < 0 && ((i0 + kk) & h_mask) == 0 && i0 + kk < A) {
+                        pend_pa = hist_bin_match(ja, PLAIN || row_ok[0], h_shift, h_lo_key, h_last, pend_ba);
+                        pend_pb = hist_bin_match(jb, PLAIN || row_ok[1], h_shift, h_lo_key, h_last, pend_bb);
+                        hist_commit(hrow, pend_ba, pend_pa, lanemask_lt);
+                        hist_commit(hrow, pend_bb, pend_pb, lanemask_lt);
+                        hrow += m.n_bins;
                     }
                     e1a *= r1a; r1a *= b1[0].q;
                     e2a *= r2a; r2a *= b2[0].q;
                     e1b *= r1b; r1b *= b1[1].q;
                     e2b *= r2b; r2b *= b2[1].q;
+                    if (kk == 7) {          // half-tile 1 of the previous chunk is reduced (garbage at c == 0: dropped); half-tile 0 is complete
+                        finish_half(i0 - 8, c > 0);
+                        __syncwarp();
+                    }
+                    if (kk == 15) {         // half-tile 0 of this chunk is reduced; half-tile 1 is complete
+                        finish_half(i0, true);
+                        __syncwarp();
+                    }
                 }
                 sweep_beam_next(b1[0]); sweep_beam_next(b2[0]);
                 sweep_beam_next(b1[1]); sweep_beam_next(b2[1]);
-                __syncwarp();
-                // column sums over the warp's 64 samples: 2 lanes per angle, 16 rows each (two independent chains per sum)
-                {
-                    double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
-                    const double2* tcol = tile + (half * 16) * kPairPitch + col;
-#pragma unroll
-                    for (int rr = 0; rr < 16; rr += 2) {
-                        const double2 va = tcol[rr * kPairPitch], vb = tcol[(rr + 1) * kPairPitch];
-                        s1a += va.x; s1b += vb.x;
-                        s2a += va.y; s2b += vb.y;
-                    }
-                    double s1 = s1a + s1b, s2 = s2a + s2b;
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-                    if (half == 0) {
-                        double2 a = acc[i0 + col];
-                        a.x += s1; a.y += s2;
-                        acc[i0 + col] = a;
-                    }
-                }
-                __syncwarp();
             }
+            // the last chunk's upper half has no sweep to hide behind
+#pragma unroll
+            for (int rr = 0; rr < 8; rr += 2) {
+                const double2 va = col1[rr * kHalfPitch], vb = col1[(rr + 1) * kHalfPitch];
+                ra1 += va.x; ra2 += va.y;
+                rb1 += vb.x; rb2 += vb.y;
+            }
+            finish_half((n_chunks - 1) * kChunk + 8, true);
         };
         if (plain)
             sweep(std::true_type{});

@@ -25,6 +25,9 @@ struct SamplerParams {
     Prior prior[15];
     unsigned long long seed;
     unsigned long long first_index;   // global index of sample 0 of this launch
+    // value = scale * u + offset, then exp() for the inputs in log_mask, Box-Muller for those in normal_mask (host-filled)
+    double scale[15], offset[15];
+    uint32_t log_mask, normal_mask;
 };
 
 // Philox4x32-10 (Salmon et al., SC'11): counter (c0..c3), key (k0, k1)
@@ -50,35 +53,83 @@ __host__ __device__ inline void uniform_pair(unsigned long long seed, unsigned l
     uint32_t o[4];
     philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), pair, stream, (uint32_t)seed, (uint32_t)(seed >> 32), o);
     const uint64_t a = ((uint64_t)o[1] << 32) | o[0], b = ((uint64_t)o[3] << 32) | o[2];
+#if defined(__CUDA_ARCH__)
+    // (double)(a >> 11) * 2^-53 without the 64-bit integer conversion: the 53 bits are split into a 21-bit and a 32-bit
+    // part, each dropped into the low mantissa word of a power of two (2^84, 2^52); the three operations below are exact
+    const uint64_t ka = a >> 11, kb = b >> 11;
+    const double ha = __hiloint2double(0x45300000, (int)(ka >> 32)) - 0x1.0p84, la = __hiloint2double(0x43300000, (int)(uint32_t)ka) - 0x1.0p52;
+    const double hb = __hiloint2double(0x45300000, (int)(kb >> 32)) - 0x1.0p84, lb = __hiloint2double(0x43300000, (int)(uint32_t)kb) - 0x1.0p52;
+    u0 = (ha + la) * 0x1.0p-53;
+    u1 = (hb + lb) * 0x1.0p-53;
+#else
     u0 = (double)(a >> 11) * 0x1.0p-53;
     u1 = (double)(b >> 11) * 0x1.0p-53;
+#endif
+}
+
+// Normal(mean a, std b): Box-Muller with a second uniform from stream 1 of the same (sample, input).  Out of line: no prior
+// of the PEM v0 plume/cathode inputs is normal, and fifteen inlined copies made up a quarter of the reduce-only kernel's code.
+__device__ __noinline__ double normal_prior(double a, double b, double u, unsigned long long seed, unsigned long long sample,
+                                            uint32_t input) {
+    double v0, v1;
+    uniform_pair(seed, sample, input, 1u, v0, v1);
+    const double r = sqrt(-2.0 * log(1.0 - u));          // 1-u in (0, 1]
+    return fma(r * cospi(2.0 * v0), b, a);
 }
 
 __device__ __forceinline__ double apply_prior(const Prior& pr, double u, unsigned long long seed, unsigned long long sample,
                                               uint32_t input) {
     switch (pr.kind) {
         case PRIOR_UNIFORM: return fma(u, pr.b - pr.a, pr.a);
-        case PRIOR_LOGUNIFORM: return exp(fma(u, pr.log_ratio, pr.log_a));
-        case PRIOR_NORMAL: {   // Box-Muller with a second uniform from stream 1 of the same (sample, input)
-            double v0, v1;
-            uniform_pair(seed, sample, input, 1u, v0, v1);
-            const double r = sqrt(-2.0 * log(1.0 - u));          // 1-u in (0, 1]
-            return fma(r * cospi(2.0 * v0), pr.b, pr.a);
-        }
+        case PRIOR_LOGUNIFORM: return fm_exp(fma(u, pr.log_ratio, pr.log_a));   // branch-free, < 1 ulp (hpem_fastmath.cuh)
+        case PRIOR_NORMAL: return normal_prior(pr.a, pr.b, u, seed, sample, input);
         default: return pr.a;
     }
 }
 
-// all 15 inputs of one sample
-__device__ __forceinline__ void sample_inputs(const SamplerParams& sp, unsigned long long local_index, double x[15]) {
-    const unsigned long long sample = sp.first_index + local_index;
+// All 15 inputs of N samples (N = 1, or the two samples a thread of the reduce-only kernel owns).  The 8 N Philox calls come
+// first, in ONE basic block, so their ten-round dependency chains interleave; then the affine maps; the exponentials of
+// the LogUniform inputs (and the rare Normal inputs) last, behind warp-uniform tests of the prior masks.  Values are
+// exactly those of apply_prior() applied input by input.
+template <int N>
+__device__ __forceinline__ void sample_inputs_n(const SamplerParams& sp, const unsigned long long (&local_index)[N], double (&x)[N][15]) {
+    double u[N][16];
 #pragma unroll
     for (uint32_t pair = 0; pair < 8; ++pair) {
-        double u0, u1;
-        uniform_pair(sp.seed, sample, pair, 0u, u0, u1);
-        x[2 * pair] = apply_prior(sp.prior[2 * pair], u0, sp.seed, sample, 2 * pair);
-        if (2 * pair + 1 < 15) x[2 * pair + 1] = apply_prior(sp.prior[2 * pair + 1], u1, sp.seed, sample, 2 * pair + 1);
+#pragma unroll
+        for (int s = 0; s < N; ++s) uniform_pair(sp.seed, sp.first_index + local_index[s], pair, 0u, u[s][2 * pair], u[s][2 * pair + 1]);
     }
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+#pragma unroll
+        for (int s = 0; s < N; ++s) x[s][k] = fma(u[s][k], sp.scale[k], sp.offset[k]);
+    }
+    if (sp.log_mask) {
+#pragma unroll
+        for (int k = 0; k < 15; ++k) {
+            if (sp.log_mask & (1u << k)) {
+#pragma unroll
+                for (int s = 0; s < N; ++s) x[s][k] = fm_exp(x[s][k]);   // branch-free, < 1 ulp (hpem_fastmath.cuh)
+            }
+        }
+    }
+    if (sp.normal_mask) {
+#pragma unroll
+        for (int k = 0; k < 15; ++k) {
+            if (sp.normal_mask & (1u << k)) {
+#pragma unroll
+                for (int s = 0; s < N; ++s)
+                    x[s][k] = normal_prior(sp.prior[k].a, sp.prior[k].b, u[s][k], sp.seed, sp.first_index + local_index[s], k);
+            }
+        }
+    }
+}
+__device__ __forceinline__ void sample_inputs(const SamplerParams& sp, unsigned long long local_index, double x[15]) {
+    const unsigned long long idx[1] = {local_index};
+    double xx[1][15];
+    sample_inputs_n<1>(sp, idx, xx);
+#pragma unroll
+    for (int k = 0; k < 15; ++k) x[k] = xx[0][k];
 }
 
 __global__ void __launch_bounds__(256) sample_inputs_kernel(const SamplerParams sp, long long n, double* o0, double* o1,

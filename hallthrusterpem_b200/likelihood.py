@@ -8,6 +8,7 @@ materialises `j_ion`: per sample only the log-likelihood (and optionally the int
 from __future__ import annotations
 
 import ctypes
+import threading
 
 import numpy as np
 
@@ -16,29 +17,57 @@ from .engine import _Batch, _is_torch_tensor as _is_torch, get_grid, torr_2_pa
 
 
 class JionMeasurements:
-    """Probe angles (rad, |theta| <= pi/2), measured j_ion and standard deviations, resident on one device."""
+    """Probe angles (rad, |theta| <= pi/2), measured j_ion and standard deviations.  `device` is one CUDA device index or
+    -- for host inputs evaluated from one process on several GPUs -- 'all' / a list; the sorted, pre-weighted probe table is
+    created on each device the first time it is used there."""
 
-    def __init__(self, theta, y, sigma, n_angles: int = 91, sweep_radius: float = 1.0, device: int | None = None):
+    def __init__(self, theta, y, sigma, n_angles: int = 91, sweep_radius: float = 1.0, device=None):
         import torch
         self.lib = _lib.load()
-        self.device = torch.cuda.current_device() if device is None else int(device)
-        self.grid = get_grid(self.device, n_angles, np.atleast_1d(np.float64(sweep_radius)))
+        if device is None:
+            self.devices = [torch.cuda.current_device()]
+        else:
+            from .engine import resolve_devices
+            self.devices = resolve_devices(device)
+        self.device = self.devices[0]
+        self.n_angles, self.sweep_radius = int(n_angles), float(sweep_radius)
         th, yy, sg = (np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1)) for v in (theta, y, sigma))
         if not (th.shape == yy.shape == sg.shape):
             raise ValueError('theta, y and sigma must have the same length')
         if np.any(np.abs(th) > np.pi / 2):
             raise ValueError('A value in x_new is outside the interpolation range.')     # what interp1d raises
         self.m = int(th.shape[0])
-        dptr = ctypes.POINTER(ctypes.c_double)
-        h = ctypes.c_void_p()
-        _lib.check(self.lib.hpem_measurements_create(self.grid.handle, self.m, th.ctypes.data_as(dptr),
-                                                     yy.ctypes.data_as(dptr), sg.ctypes.data_as(dptr), ctypes.byref(h)))
-        self._h = h
+        self._arrays = (th, yy, sg)
+        self._handles: dict[int, tuple] = {}
+        self._lock = threading.Lock()
+        self.on(self.device)
+
+    def on(self, dev: int):
+        """(grid handle, measurement handle) on device `dev`."""
+        with self._lock:
+            got = self._handles.get(dev)
+            if got is None:
+                grid = get_grid(dev, self.n_angles, np.atleast_1d(np.float64(self.sweep_radius)))
+                th, yy, sg = self._arrays
+                dptr = ctypes.POINTER(ctypes.c_double)
+                h = ctypes.c_void_p()
+                _lib.check(self.lib.hpem_measurements_create(grid.handle, self.m, th.ctypes.data_as(dptr),
+                                                             yy.ctypes.data_as(dptr), sg.ctypes.data_as(dptr), ctypes.byref(h)))
+                got = self._handles[dev] = (grid, h)
+            return got
+
+    @property
+    def grid(self):
+        return self.on(self.device)[0]
+
+    @property
+    def _h(self):
+        return self.on(self.device)[1]
 
     def close(self):
-        if getattr(self, '_h', None):
-            self.lib.hpem_measurements_destroy(self._h)
-            self._h = None
+        for _, h in getattr(self, '_handles', {}).values():
+            self.lib.hpem_measurements_destroy(h)
+        self._handles = {}
 
     def __del__(self):
         try:
@@ -47,29 +76,63 @@ class JionMeasurements:
             pass
 
 
-def jion_log_likelihood(inputs: dict, meas: JionMeasurements, *, torr: float | None = None, return_pred: bool = False):
-    """Gaussian log-likelihood of the probe data under the plume model for every sample of `inputs`
-    (torch CUDA float64 tensors -> torch results on the device; NumPy arrays / scalars -> NumPy results).  Returns the
-    log-likelihood of loop shape (and the interpolated predictions, loop shape + (m,), with `return_pred`)."""
+def _loglike_on_device(batch: _Batch, meas: JionMeasurements, dev: int, torr: float | None, return_pred: bool):
     import torch
-    batch = _Batch(inputs, _lib.PLUME_INPUTS)
-    if not batch.on_device:        # NumPy / scalar inputs (an MCMC step): through the device, NumPy back
-        moved = {k: (torch.as_tensor(np.asarray(inputs[k], dtype=np.float64), device=f'cuda:{meas.device}')
-                     if np.ndim(inputs[k]) > 0 else inputs[k]) for k in _lib.PLUME_INPUTS}
-        if not any(_is_torch(v) for v in moved.values()):      # all scalars: one sample
-            moved['P_b'] = torch.as_tensor(np.atleast_1d(np.float64(inputs['P_b'])), device=f'cuda:{meas.device}')
-        res = jion_log_likelihood(moved, meas, torr=torr, return_pred=return_pred)
-        return tuple(r.cpu().numpy() for r in res) if return_pred else res.cpu().numpy()
-    if batch.device_index != meas.device:
-        raise ValueError('jion_log_likelihood expects inputs on the device of the measurement set')
-    dev = f'cuda:{meas.device}'
-    ll = torch.empty(batch.out_shape, dtype=torch.float64, device=dev)
-    pred = torch.empty(batch.out_shape + (meas.m,), dtype=torch.float64, device=dev) if return_pred else None
-    stream = torch.cuda.current_stream(meas.device).cuda_stream
-    _lib.check(meas.lib.hpem_loglike(meas.grid.handle, meas._h, batch.n, ctypes.byref(batch.struct),
+    grid, h = meas.on(dev)
+    ll = torch.empty(batch.out_shape, dtype=torch.float64, device=f'cuda:{dev}')
+    pred = torch.empty(batch.out_shape + (meas.m,), dtype=torch.float64, device=f'cuda:{dev}') if return_pred else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(meas.lib.hpem_loglike(grid.handle, h, batch.n, ctypes.byref(batch.struct),
                                      torr_2_pa() if torr is None else float(torr), ctypes.c_void_p(ll.data_ptr()),
                                      ctypes.c_void_p(pred.data_ptr()) if return_pred else None, ctypes.c_void_p(stream)))
     return (ll, pred) if return_pred else ll
+
+
+def jion_log_likelihood(inputs: dict, meas: JionMeasurements, *, torr: float | None = None, return_pred: bool = False):
+    """Gaussian log-likelihood of the probe data under the plume model for every sample of `inputs`
+    (torch CUDA float64 tensors -> torch results on the device; NumPy arrays / scalars -> NumPy results).  Returns the
+    log-likelihood of loop shape (and the interpolated predictions, loop shape + (m,), with `return_pred`).
+    Host inputs with a measurement set created for several devices are sharded over them from this one process."""
+    import torch
+    batch = _Batch(inputs, _lib.PLUME_INPUTS)
+    if batch.on_device:
+        if batch.device_index not in meas.devices:
+            raise ValueError('jion_log_likelihood expects inputs on a device of the measurement set')
+        return _loglike_on_device(batch, meas, batch.device_index, torr, return_pred)
+
+    # NumPy / scalar inputs (an MCMC step): through the device(s), NumPy back
+    host = {k: np.asarray(inputs[k], dtype=np.float64) for k in _lib.PLUME_INPUTS}
+    n, shape = batch.n, batch.out_shape
+    flat = {k: (np.ascontiguousarray(np.broadcast_to(v, shape)).reshape(-1) if v.size > 1 else v.reshape(-1)) for k, v in host.items()}
+    ll = np.empty(n)
+    pred = np.empty((n, meas.m)) if return_pred else None
+    from .engine import _thread_pool
+    from .synthetic import shard_bounds
+    devs = meas.devices if n >= 64 * len(meas.devices) else meas.devices[:1]
+
+    def one(r):
+        lo, hi = shard_bounds(n, len(devs), r)
+        if hi <= lo:
+            return
+        d = devs[r]
+        with torch.cuda.device(d):
+            part = {k: (torch.as_tensor(v[lo:hi]).to(f'cuda:{d}', non_blocking=True) if v.size > 1 else float(v[0]))
+                    for k, v in flat.items()}
+            if not any(_is_torch(v) for v in part.values()):      # all scalars: one sample
+                part['P_b'] = torch.full((hi - lo,), float(flat['P_b'][0]), dtype=torch.float64, device=f'cuda:{d}')
+            res = _loglike_on_device(_Batch(part, _lib.PLUME_INPUTS), meas, d, torr, return_pred)
+            if return_pred:
+                ll[lo:hi] = res[0].cpu().numpy()
+                pred[lo:hi] = res[1].cpu().numpy()
+            else:
+                ll[lo:hi] = res.cpu().numpy()
+
+    if len(devs) == 1:
+        one(0)
+    else:
+        list(_thread_pool().map(one, range(len(devs))))
+    ll = ll.reshape(shape)
+    return (ll, pred.reshape(shape + (meas.m,))) if return_pred else ll
 
 
 def marginal_log_likelihood(loglike):

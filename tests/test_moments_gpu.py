@@ -39,7 +39,7 @@ def test_moments_match_materialised_path(n, n_angles, chunks, cuda_device):
     np.testing.assert_allclose(res.sums[L.off_angle_sum:L.off_angle_sumsq], sums[L.off_angle_sum:L.off_angle_sumsq], rtol=1e-12)
     np.testing.assert_allclose(res.sums[L.off_angle_sumsq:L.off_hist], sums[L.off_angle_sumsq:L.off_hist], rtol=1e-11)
     assert np.array_equal(res.sums[L.off_hist:], sums[L.off_hist:]), 'histogram counts differ'
-    np.testing.assert_allclose(res.minmax, minmax, rtol=1e-13)
+    np.testing.assert_allclose(res.minmax, minmax, rtol=1e-12)     # (K1u's quad-row mode sums num/den in another order: arccos amplifies)
     assert res.histograms.sum(axis=1).tolist() == [n] * L.n_hist_angles
     # decoded statistics against NumPy on the materialised arrays
     np.testing.assert_allclose(res.j_mean, out['j_ion'].mean(axis=0), rtol=1e-12)

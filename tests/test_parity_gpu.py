@@ -46,7 +46,9 @@ def test_golden_host_path(path, mode, cuda_device):
     out = plume_cathode(inputs, sweep, n_angles=meta['n_angles'], torr_2_pa=meta['torr_2_pa'], extras=True, **MODES[mode])
     assert isinstance(out['j_ion'], np.ndarray) and out['j_ion'].dtype == np.float64
     frac = _compare(out, g, inputs, meta['torr_2_pa'], radii, path.stem)
-    assert frac > 0.98, f'only {frac:.4f} of j_ion meets the pure rel-1e-12 rule'
+    # measured: 99.997 % of all elements meet the PURE rel-1e-12 rule (the floor is only for thin-CEX far wings); the
+    # hand-built edge rows (needle beams, opaque / transparent CEX ...) sit on the floor by construction
+    assert frac >= (0.98 if path.stem.startswith('edge') else 0.9995), f'only {frac:.5f} of j_ion meets the pure rel-1e-12 rule'
     coords = out['j_ion_coords']
     assert coords.dtype == object and coords.shape == g['div_angle'].shape[:1]
     assert np.array_equal(coords[0], np.linspace(0, np.pi / 2, meta['n_angles']))
@@ -126,24 +128,31 @@ def test_fast_and_direct_kernels_agree_large(cuda_device):
 
 
 def test_config3_h9_pressure_sweep_large(cuda_device):
-    """BASELINE config 3 shape (H9-style linear pressure sweep incl. P_b = 0, A = 256 -> even-count Simpson tail) at
-    2e6 samples on the device: recurrence kernels vs the direct kernel everywhere, vs the CPU oracle on a strided subsample."""
+    """BASELINE config 3 at its stated size (H9-style linear pressure sweep incl. P_b = 0, 1e7 samples x 256 angles -> 20.5 GB
+    of j_ion, even-count Simpson tail) on the device: recurrence kernels vs the direct kernel everywhere, vs the CPU oracle
+    on a strided subsample."""
     import torch
     from hallthrusterpem_b200.synthetic import h9_sweep_batch
     from oracle.ref_restated import current_density_oracle
     _, current_density, _ = _models()
-    n, A = 2_000_000, 256
+    n, A = 10_000_000, 256
     host = h9_sweep_batch(n, 77)
     b = {k: torch.as_tensor(v, device='cuda:0') for k, v in host.items()}
     fast = current_density(b, 1.0, n_angles=A, extras=True)
     jf = fast['j_ion']
+    assert jf.shape == (n, A) and jf.numel() * 8 > 20e9
     for kw in ({'direct': True}, {'lanes4': True}):
         other = current_density(b, 1.0, n_angles=A, extras=True, **kw)
-        assert ((jf - other['j_ion']).abs() / other['j_ion'].abs()).max().item() < 3e-13
+        worst = 0.0
+        for lo in range(0, n, 1_000_000):       # compare in slices: the temporaries of one 20 GB comparison would not fit twice
+            a, o = jf[lo:lo + 1_000_000], other['j_ion'][lo:lo + 1_000_000]
+            worst = max(worst, ((a - o).abs() / o.abs()).max().item())
+        assert worst < 3e-13, worst
         assert torch.equal(fast['invalid'], other['invalid'])
         assert ((fast['cos_div'] - other['cos_div']).abs() / other['cos_div'].abs()).max().item() < 1e-13
-        del other
-    idx = np.arange(0, n, 997)
+        del other, a, o
+        torch.cuda.empty_cache()
+    idx = np.arange(0, n, 4999)
     sub = {k: v[idx] for k, v in host.items()}
     with np.errstate(all='ignore'):
         ref = current_density_oracle(sub, 1.0, A, 133.322, with_coords=False, return_internals=True)

@@ -40,16 +40,23 @@ def test_sampled_moments_equal_sample_then_accumulate_and_are_shard_invariant(cu
     b.accumulate(sample_inputs(n, seed, 0, device=0))
     torch.cuda.synchronize()
     ra, rb = a.result(), b.result()
-    assert np.array_equal(ra.sums, rb.sums) and np.array_equal(ra.minmax, rb.minmax)     # same values, same kernel, same order
-    # three uneven shards of the same global index range, accumulated separately and merged by addition
+    # same values, same arithmetic, same order: counts, histograms and min/max are identical; the two template instantiations
+    # of the kernel may round a handful of the 412 per-angle sums differently in the last bit
+    L0 = a.layout
+    assert np.array_equal(ra.sums[:3], rb.sums[:3]) and np.array_equal(ra.sums[L0.off_hist:], rb.sums[L0.off_hist:])
+    assert np.array_equal(ra.minmax, rb.minmax)
+    np.testing.assert_allclose(ra.sums, rb.sums, rtol=1e-14)
+    # three uneven shards of the same global index range, accumulated separately and merged (pairwise, centred moments)
+    from hallthrusterpem_b200.mc import merge_packed_host
     parts = []
     for lo, hi in ((0, 7001), (7001, 19000), (19000, n)):
         m = MonteCarloMoments(n_angles=A, hist=hist, device=0, torr=133.322)
         m.accumulate_sampled(hi - lo, seed, lo)
-        parts.append(m.result())
-    sums = sum(p.sums for p in parts)
+        parts.append(m.packed.cpu().numpy())
     L = a.layout
+    merged = merge_packed_host(L, np.stack(parts))
+    sums, minmax = merged[:L.n_sums], merged[L.n_sums:]
     assert np.array_equal(sums[:3], ra.sums[:3]) and np.array_equal(sums[L.off_hist:], ra.sums[L.off_hist:])
     np.testing.assert_allclose(sums, ra.sums, rtol=1e-12)
-    assert np.array_equal(np.max([p.minmax for p in parts], axis=0), ra.minmax)
+    assert np.array_equal(minmax, ra.minmax)
     assert ra.n_samples == n and ra.n_invalid == 0
