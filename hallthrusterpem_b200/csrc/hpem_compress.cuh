@@ -69,17 +69,19 @@ __global__ void __launch_bounds__(kThreadsC) latent_kernel(const EvalParams p, c
     double x_in[kNumInputs];
 #pragma unroll
     for (int q = 0; q < kNumInputs; ++q) x_in[q] = (q == IN_P_b || (q > IN_P_T && q != IN_T)) ? load_in(p, q, s) : 0.0;
-    const SampleConsts k = plume_sample_consts(x_in[IN_P_b], x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3],
-                                               x_in[IN_c4], x_in[IN_c5], p.torr);
+    SampleConsts k;
     double j_cex, base;
-    cex_terms(k.density, x_in[IN_sigma], x_in[IN_I_B0], p.radius0, j_cex, base);
     BeamState b1, b2;
-    beam_init(b1, p.h, k.a1, __dmul_rn(base, k.amp1));
-    beam_init(b2, p.h, k.a2, __dmul_rn(base, k.amp2));
+    const bool fast = plume_prologue(p, x_in, k, j_cex, base, b1, b2);
 
     // plume.py:105-106: invalid samples return 1e-20 at every angle -- that row is what gets normalised and projected
     bool invalid = (k.a1 <= 0.0);
-    if (!invalid && !(b1.amp >= 0.0 && b2.amp >= 0.0 && j_cex > 0.0)) invalid = lookahead_nonpositive(b1, b2, j_cex, A);
+    const bool ordinary = b1.amp >= 0.0 && b2.amp >= 0.0 && j_cex > 0.0;
+    if (!invalid && !ordinary) invalid = lookahead_nonpositive(b1, b2, j_cex, A);
+    // Warps whose rows are all ordinary (finite positive amplitudes, a normal CEX floor: every j_ion is a positive normal
+    // number) take the branch-free logarithm: sixteen independent log10 per chunk schedule as one block of fp64 work
+    // instead of sixteen libdevice calls with a special-case branch each.
+    const bool fast_log = fast && bp.norm_log10 && __all_sync(__activemask(), !invalid && ordinary && fm_mid(j_cex) && fm_mid0(b1.amp) && fm_mid0(b2.amp));
 
     double z[RK];
 #pragma unroll
@@ -93,6 +95,21 @@ __global__ void __launch_bounds__(kThreadsC) latent_kernel(const EvalParams p, c
         }
         double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec, r1 = b1.rc, r2 = b2.rc;
         const int kcount = min(kChunk, A - i0);
+        if (fast_log && kcount == kChunk) {
+#pragma unroll
+            for (int kk = 0; kk < kChunk; ++kk) {
+                const double x = fm_log10((e1 + e2) + j_cex);
+                const double2* u = reinterpret_cast<const double2*>(usm + (i0 + kk) * RK);   // broadcast loads
+#pragma unroll
+                for (int r = 0; r < RK; r += 2) {
+                    const double2 uu = u[r >> 1];
+                    z[r] = fma(uu.x, x, z[r]);
+                    z[r + 1] = fma(uu.y, x, z[r + 1]);
+                }
+                e1 *= r1; r1 *= b1.q;
+                e2 *= r2; r2 *= b2.q;
+            }
+        } else
         for (int kk = 0; kk < kcount; ++kk) {
             const double j = invalid ? kInvalidFill : (e1 + e2) + j_cex;
             const double x = bp.norm_log10 ? log10(j) : j;
@@ -128,13 +145,36 @@ __global__ void __launch_bounds__(kThreadsC) compress_field_kernel(const double*
     double z[RK];
 #pragma unroll
     for (int r = 0; r < RK; ++r) z[r] = 0.0;
-    for (int i = lane; i < bp.dof; i += 32) {
-        const double v = __ldcs(f + i);
-        const double x = bp.norm_log10 ? log10(v) : v;
+    auto project = [&](int i, double x) {
         const double* u = bp.basis_t + i;
 #pragma unroll
         for (int r = 0; r < RK; ++r)
             if (r < bp.rank) z[r] = fma(__ldg(u + (long long)r * bp.dof), x, z[r]);
+    };
+    // four elements per lane and trip (warp-uniform trip count): when all 128 of them are positive normal numbers (any j_ion
+    // the plume model returns) the four logarithms are the branch-free ones and schedule as one block; anything else takes
+    // libdevice's log10
+    int i = lane;
+    for (int i0 = 0; i0 + 128 <= bp.dof; i0 += 128, i += 128) {
+        double v[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[t] = __ldcs(f + i + 32 * t);
+        if (bp.norm_log10) {
+            const bool ok = fm_mid(v[0]) && v[0] > 0.0 && fm_mid(v[1]) && v[1] > 0.0 && fm_mid(v[2]) && v[2] > 0.0 && fm_mid(v[3]) && v[3] > 0.0;
+            if (__all_sync(0xffffffffu, ok)) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) v[t] = fm_log10(v[t]);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) v[t] = log10(v[t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) project(i + 32 * t, v[t]);
+    }
+    for (; i < bp.dof; i += 32) {
+        const double v = __ldcs(f + i);
+        project(i, bp.norm_log10 ? log10(v) : v);
     }
 #pragma unroll
     for (int r = 0; r < RK; ++r) z[r] = warp_sum(z[r]);
@@ -176,6 +216,8 @@ __global__ void __launch_bounds__(kThreadsR) reconstruct_kernel(const double* __
                 x = fma(u[r], zz.x, x);
                 x = fma(u[r + 1], zz.y, x);
             }
+            // (libdevice's exp10 stays: a branch-free 10^x through fm_exp measured 25 % slower here -- the kernel is bound by
+            //  fp64 issue, not by latency, and exp10's table-free core is shorter than exp(x ln10) with a compensated product)
             __stcs(out + (long long)s * bp.dof, bp.norm_log10 ? exp10(x) : x);
         }
     }

@@ -224,6 +224,27 @@ __device__ __forceinline__ void beam_next_chunk(BeamState& b) {
     b.rc *= b.qk;
 }
 
+// Plume part of the per-sample prologue (plume.py:40-98 + recurrence start values) for kernels that run one thread per
+// sample and may have retired lanes: branch-free back end when every ACTIVE lane of the warp is in the nominal range,
+// libdevice otherwise.  Returns which one ran.
+__device__ __forceinline__ bool plume_prologue(const EvalParams& p, const double* x_in, SampleConsts& k, double& j_cex,
+                                               double& base, BeamState& b1, BeamState& b2) {
+    const bool nominal = prologue_nominal(x_in, p.torr, false, true, p.radius0);
+    const bool fast = __all_sync(__activemask(), nominal) && !p.no_fastmath;
+    if (fast) {
+        k = plume_sample_consts<true>(x_in[IN_P_b], x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3], x_in[IN_c4], x_in[IN_c5], p.torr);
+        cex_terms<true>(k.density, x_in[IN_sigma], x_in[IN_I_B0], p.radius0, j_cex, base);
+        beam_init<true>(b1, p.h, k.a1, __dmul_rn(base, k.amp1));
+        beam_init<true>(b2, p.h, k.a2, __dmul_rn(base, k.amp2));
+    } else {
+        k = plume_sample_consts<false>(x_in[IN_P_b], x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3], x_in[IN_c4], x_in[IN_c5], p.torr);
+        cex_terms<false>(k.density, x_in[IN_sigma], x_in[IN_I_B0], p.radius0, j_cex, base);
+        beam_init<false>(b1, p.h, k.a1, __dmul_rn(base, k.amp1));
+        beam_init<false>(b2, p.h, k.a2, __dmul_rn(base, k.amp2));
+    }
+    return fast;
+}
+
 #ifndef HPEM_MIN_BLOCKS_U
 #define HPEM_MIN_BLOCKS_U (384 / HPEM_THREADS_U)      // 12 resident warps per SM with two staging buffers per warp
 #endif
@@ -1404,13 +1425,10 @@ __global__ void __launch_bounds__(kThreadsL) loglike_kernel(const EvalParams p, 
     double x_in[kNumInputs];
 #pragma unroll
     for (int q = 0; q < kNumInputs; ++q) x_in[q] = (q == IN_P_b || (q > IN_P_T && q != IN_T)) ? load_in(p, q, s) : 0.0;
-    const SampleConsts k = plume_sample_consts(x_in[IN_P_b], x_in[IN_c0], x_in[IN_c1], x_in[IN_c2], x_in[IN_c3],
-                                               x_in[IN_c4], x_in[IN_c5], p.torr);
+    SampleConsts k;
     double j_cex, base;
-    cex_terms(k.density, x_in[IN_sigma], x_in[IN_I_B0], p.radius0, j_cex, base);
     BeamState b1, b2;
-    beam_init(b1, p.h, k.a1, __dmul_rn(base, k.amp1));
-    beam_init(b2, p.h, k.a2, __dmul_rn(base, k.amp2));
+    plume_prologue(p, x_in, k, j_cex, base, b1, b2);
     const int n_chunks = (A + kChunk - 1) / kChunk;
 
     // plume.py:105-106: invalid samples return j_ion == 1e-20 at every angle -- that is what gets interpolated

@@ -91,6 +91,15 @@ int main() {
            hpem::fm_acos(-1.0), hpem::fm_acos(0.0), hpem::fm_acos(1.0000001), hpem::fm_acos(NAN));
     if (hpem::fm_acos(1.0) != 0.0 || !std::isnan(hpem::fm_acos(1.0000001)) || !std::isnan(hpem::fm_acos(NAN)) ||
         hpem::fm_acos(-1.0) != std::acos(-1.0) || hpem::fm_acos(0.0) != std::acos(0.0)) ++fails;
+    // log10 over j_ion's range (latent / compress_field kernels)
+    worst = 0;
+    for (int i = 0; i < 2000000; ++i) {
+        const double y = std::pow(10.0, -22.0 + 28.0 * U(rng));
+        const double e = ulp_err(hpem::fm_log10(y), log10l((long double)y));
+        if (e > worst) worst = e;
+    }
+    printf("fm_log10 y in [1e-22, 1e6]: worst %.4f ulp\n", worst);
+    if (worst > 1.8) ++fails;
     // sqrt
     worst = 0;
     for (int i = 0; i < 2000000; ++i) {
