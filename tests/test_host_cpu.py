@@ -377,3 +377,19 @@ def test_empty_batch_raises_like_the_reference():
         current_density_oracle(empty, 1.0, 91)
     with pytest.raises(ValueError):
         current_density(empty)
+
+
+def test_branch_free_elementary_functions_meet_their_ulp_bounds(tmp_path):
+    """csrc/hpem_fastmath.cuh compiled for the HOST (same source the kernels inline; the hardware reciprocal / rsqrt seeds are
+    emulated by 20-bit truncations) against x87 long double libm: exp < 1 ulp and correctly rounded for |x| << 1, log < 1 ulp,
+    acos < 1.25 ulp, div / sqrt correctly rounded, special values (tools/fastmath_check.cpp)."""
+    import shutil
+    import subprocess
+    gxx = shutil.which('g++')
+    if gxx is None:
+        pytest.skip('no g++')
+    exe = tmp_path / 'fastmath_check'
+    subprocess.run([gxx, '-O2', '-mfma', '-ffp-contract=off', '-DHPEM_CHECK_N=200000', '-o', str(exe),
+                    str(ROOT / 'tools' / 'fastmath_check.cpp')], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.strip().endswith('ok'), res.stdout
