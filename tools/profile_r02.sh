@@ -17,5 +17,9 @@ for k in k1u k1q k2s k3 k4; do
   $T python tools/prof_target.py $k > $O/plain_$k.log 2>&1 && \
     $T ncu --set full --clock-control none --import-source on -k regex:$pat -s 2 -c 1 -o $O/prof_r02_$k -f python tools/prof_target.py $k > $O/ncu_$k.log 2>&1
   tail -1 $O/ncu_$k.log
+  # summarise on the box (the reports together exceed what gpurun copies back); keep the two headline reports
+  python tools/ncu_summary.py $O/prof_r02_$k.ncu-rep --top 14 > $O/r02_${k}_ncu_summary.txt 2>&1
+  python tools/ncu_lines.py $O/prof_r02_$k.ncu-rep --top 25 >> $O/r02_${k}_ncu_summary.txt 2>&1
+  case $k in k1u|k2s) ;; *) rm -f $O/prof_r02_$k.ncu-rep;; esac
 done
 echo done
