@@ -2,8 +2,8 @@
 /root/reference/scripts/gen_data.py:238, over the priors of scripts/pem_v0/pem_v0_SPT-100.yml).
 
 Counter-based Philox4x32-10: the 15 inputs of global sample index i are a pure function of (seed, i), so any sharding
-of an index range over GPUs / chunks reproduces the unsharded draw.  `philox_uniforms` is the NumPy statement of the
-same stream (used by the CPU tests; the draws themselves happen in libhpem)."""
+of an index range over GPUs / chunks reproduces the unsharded draw.  The draws happen in libhpem; the NumPy statement of the
+same stream that the tests check them against lives with the other checkers, in oracle/sampler_oracle.py."""
 from __future__ import annotations
 
 import ctypes
@@ -53,57 +53,4 @@ def sample_inputs(n: int, seed: int, first_index: int = 0, priors: dict = SPT100
         ptrs[k] = out[name].data_ptr() if name in out else None
     stream = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(lib.hpem_sample_inputs(dev, n, seed, first_index, priors_struct(priors), ptrs, ctypes.c_void_p(stream)))
-    return out
-
-
-# ------------------------------------------------------------------------------------------------
-# NumPy statement of the stream (CPU tests)
-# ------------------------------------------------------------------------------------------------
-def philox4x32_10(c0, c1, c2, c3, k0, k1):
-    """Vectorised Philox4x32-10 on uint32 arrays (uint64 intermediates)."""
-    m0, m1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
-    w0, w1 = 0x9E3779B9, 0xBB67AE85
-    mask = np.uint64(0xFFFFFFFF)
-    c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint64) for x in (c0, c1, c2, c3))
-    k0, k1 = int(k0), int(k1)
-    for _ in range(10):
-        p0, p1 = m0 * c0, m1 * c2
-        n0 = (p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0)
-        n1 = p1 & mask
-        n2 = (p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1)
-        n3 = p0 & mask
-        c0, c1, c2, c3 = n0, n1, n2, n3
-        k0, k1 = (k0 + w0) & 0xFFFFFFFF, (k1 + w1) & 0xFFFFFFFF
-    return c0, c1, c2, c3
-
-
-def philox_uniforms(seed: int, first_index: int, n: int) -> np.ndarray:
-    """(n, 16) uniforms in [0, 1): column k is the uniform behind input k (column 15 is unused)."""
-    idx = np.uint64(first_index) + np.arange(n, dtype=np.uint64)
-    lo, hi = idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32)
-    out = np.empty((n, 16))
-    for pair in range(8):
-        o0, o1, o2, o3 = philox4x32_10(lo, hi, np.full(n, pair, np.uint64), np.zeros(n, np.uint64),
-                                       seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-        a, b = (o1 << np.uint64(32)) | o0, (o3 << np.uint64(32)) | o2
-        out[:, 2 * pair] = (a >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
-        out[:, 2 * pair + 1] = (b >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
-    return out
-
-
-def apply_priors_numpy(u: np.ndarray, priors: dict = SPT100_PRIORS) -> dict:
-    """Uniform / LogUniform / const transforms of `philox_uniforms` columns (Normal needs the second stream; not restated)."""
-    out = {}
-    for k, name in enumerate(_lib.INPUT_NAMES):
-        if name not in priors:
-            continue
-        kind, a, b = priors[name]
-        if kind == 'uniform':
-            out[name] = u[:, k] * (b - a) + a
-        elif kind == 'loguniform':
-            out[name] = np.exp(u[:, k] * (np.log(b) - np.log(a)) + np.log(a))
-        elif kind == 'const':
-            out[name] = np.full(u.shape[0], float(a))
-        else:
-            raise NotImplementedError(kind)
     return out

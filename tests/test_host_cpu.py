@@ -163,7 +163,8 @@ def test_synthetic_batches_and_sharding():
 def test_philox_known_answers_and_uniforms():
     """The NumPy statement of the sampler's stream reproduces the published Philox4x32-10 known-answer vectors
     (Random123 kat_vectors); the device code is the same function compiled by nvcc (tests/test_sampler_gpu.py)."""
-    from hallthrusterpem_b200.sampler import SPT100_PRIORS, apply_priors_numpy, philox4x32_10, philox_uniforms
+    from hallthrusterpem_b200.sampler import SPT100_PRIORS
+    from oracle.sampler_oracle import apply_priors_numpy, philox4x32_10, philox_uniforms
     kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
            ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),

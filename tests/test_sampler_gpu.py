@@ -6,10 +6,11 @@ pytestmark = pytest.mark.gpu
 
 
 def test_device_sampler_matches_numpy_stream(cuda_device):
-    from hallthrusterpem_b200.sampler import SPT100_PRIORS, apply_priors_numpy, philox_uniforms, sample_inputs
+    from hallthrusterpem_b200.sampler import SPT100_PRIORS, sample_inputs
+    from oracle.sampler_oracle import apply_priors_numpy, philox_uniforms
     n, seed, first = 20000, 987654321012345, 4_000_000_123
     dev = sample_inputs(n, seed, first, device=0)
-    ref = apply_priors_numpy(philox_uniforms(seed, first, n))
+    ref = apply_priors_numpy(philox_uniforms(seed, first, n), SPT100_PRIORS)
     assert set(dev) == set(SPT100_PRIORS)
     for name, t in dev.items():
         got = t.cpu().numpy()
