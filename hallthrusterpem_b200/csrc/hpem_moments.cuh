@@ -16,10 +16,8 @@
 // per-warp accumulators; one partial vector per block at the end, merged in block order by moments_finalize_kernel
 // (bit-reproducible for a fixed launch geometry).
 //
-// Histograms: log-linear bins straight from the leading bits of the fp64 pattern (no log).  The 32 lanes of a warp
-// look at the SAME angle, and a population occupies few bins there, so lane-wise atomics would serialise; instead
-// __match_any_sync groups the lanes by bin and the lowest lane of each group adds the group size with ONE reduction
-// to the block's private histogram in global memory (L2 atomics; blocks never share a line).
+// Histograms: log-linear bins straight from the leading bits of the fp64 pattern (no log), one fire-and-forget reduction
+// per lane to the block's private histogram in global memory (L2 atomics; blocks never share a line) -- see hist_add.
 //
 // Second moments are kept CENTRED: a block's raw sums become (n, S, M2 = Q - S^2/n) and are merged with Chan's
 // pairwise update, block after block, call after call, rank after rank -- the variance of the whole population never
@@ -46,9 +44,6 @@ struct MomentsParams {
 constexpr int kMomScalars = 12;  // n_samples n_invalid n_nonfinite_rows | {n_finite sum M2} x {V_cc div_angle T_c}
 #ifndef HPEM_THREADS_M
 #define HPEM_THREADS_M 384
-#endif
-#ifndef HPEM_HIST_LAG
-#define HPEM_HIST_LAG 5          // recurrence steps between a histogram MATCH and the use of its result
 #endif
 constexpr int kThreadsM = HPEM_THREADS_M;   // upper bound; the launch picks the warp count that fits shared memory
 constexpr int kMaxWarpsM = kThreadsM / 32;
@@ -89,17 +84,17 @@ __device__ __forceinline__ void sweep_beam_next(SweepBeam& b) {
     b.rc *= b.qk;
 }
 
-// Histogram update of the warp in two halves, so that the latency of MATCH (the slowest instruction of the sweep) is covered
-// by the recurrence steps between them.  hist_bin_match: log-linear bin of j and the mask of lanes in the same bin;
-// hist_commit: the lowest lane of every group adds the group size to the block's histogram row (one reduction per bin).
-__device__ __forceinline__ unsigned hist_bin_match(double j, bool ok, int h_shift, int h_lo_key, int h_last, int& b) {
-    // octave from the exponent field, 2^sub_bits linear sub-bins from the leading mantissa bits.
-    // bin 0 = underflow (incl. zero/negative: the shifted pattern is negative), last bin = overflow (incl. +inf)
-    b = min(max((__double2hiint(j) >> h_shift) - h_lo_key, 0), h_last);
-    return ok ? __match_any_sync(0xffffffffu, b) & ~0u : (__match_any_sync(0xffffffffu, -1), 0u);
-}
-__device__ __forceinline__ void hist_commit(unsigned* hrow, int b, unsigned peers, unsigned lanemask_lt) {
-    if (peers != 0u && (peers & lanemask_lt) == 0u) atomicAdd(hrow + b, (unsigned)__popc(peers));
+// One histogram update: log-linear bin of j (octave from the exponent field, 2^sub_bits linear sub-bins from the leading
+// mantissa bits; bin 0 = underflow incl. zero / negative -- the shifted pattern is negative --, last bin = overflow incl.
+// +inf) and ONE reduction per lane to the block's private histogram row in global memory.  The 32 lanes of a warp look at
+// the same angle and a population occupies few bins there; the L2 atomic units absorb that (fire-and-forget RED, no
+// return value, blocks never share a line).  Measured against the alternatives on B200, 256 angles, histogram every 8th:
+// per-lane shared-memory atomics serialise on the hot bins (44 % of the first version of this kernel), per-warp slot
+// buffers cost 4 instructions per angle step (round 1), __match_any_sync aggregation + one RED per group waits ~200
+// cycles for MATCH even when its result is consumed five steps later (7.35e11 evals/s); plain per-lane REDs: 7.77e11.
+__device__ __forceinline__ void hist_add(unsigned* hrow, double j, bool ok, int h_shift, int h_lo_key, int h_last) {
+    const int b = min(max((__double2hiint(j) >> h_shift) - h_lo_key, 0), h_last);
+    if (ok) atomicAdd(hrow + b, 1u);
 }
 
 // HS: histogram angle stride known at compile time (8, the default), 0 = no histograms, -1 = any power-of-two stride.
@@ -134,7 +129,6 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
     const int h_lo_key = ((m.hist_min_exp2 + 1023) << m.hist_sub_bits) - 1;
     const int h_mask = max(m.hist_stride, 1) - 1;
     unsigned* hist_blk = m.hist_partials + (size_t)blockIdx.x * m.n_hist_angles * m.n_bins;
-    const unsigned lanemask_lt = (1u << lane) - 1u;
 
     const long long batch = (long long)n_warps * 64;
     for (long long b0 = (long long)blockIdx.x * batch; b0 < p.n; b0 += (long long)gridDim.x * batch) {
@@ -249,33 +243,29 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
         // warps whose 64 rows are all ordinary (finite, valid) -- virtually all of them -- skip the per-element selects
         const bool plain = !__any_sync(0xffffffffu, invalid[0] || invalid[1] || !row_ok[0] || !row_ok[1]);
         // The 16-angle chunk goes through shared memory as two half-tiles of 8 angles, [32 rows][kHalfPitch] (t, q) pairs each.
-        // While a thread sweeps one half it column-reduces the OTHER one, one row per recurrence step, so the loads and
+        // While a thread sweeps one half it column-reduces the OTHER one, two rows per recurrence step, so the loads and
         // additions of the reduction are scheduled inside the fp64 stream of the sweep instead of forming a latency-bound
-        // phase of their own between two warp barriers.  Lane (c8 = lane & 7, q4 = lane >> 3) sums column c8 over rows 8 q4 .. 8 q4 + 7.
+        // phase of their own between two warp barriers.  Seen as doubles a half-tile has 16 columns (8 angles x {t, q}):
+        // lane (c16 = lane & 15, h = lane >> 4) sums column c16 over rows 16 h .. 16 h + 15 with 8-byte loads (a half-warp
+        // reads 128 contiguous bytes), ONE shuffle joins the two row halves, and lanes 0-15 add to the per-warp accumulators.
+        // (A first version used 16-byte loads with lane = (angle, row quarter): two shuffle stages and a 8-lane update per
+        //  half cost 26 % of the loop, tools/sweep_probe2.cu.)
         double2* my0 = tile + lane * kHalfPitch;                        // this thread's row in half-tile 0 (angles 0-7 of a chunk)
         double2* my1 = my0 + 32 * kHalfPitch;                           // ... in half-tile 1 (angles 8-15)
-        const int c8 = lane & 7, q4 = lane >> 3;
-        const double2* col0 = tile + (q4 * 8) * kHalfPitch + c8;
-        const double2* col1 = col0 + 32 * kHalfPitch;
+        const int c16 = lane & 15, rh = lane >> 4;
+        const double* col0 = reinterpret_cast<const double*>(tile) + (rh * 16) * (2 * kHalfPitch) + c16;
+        const double* col1 = col0 + 32 * (2 * kHalfPitch);
+        double* acc_d = reinterpret_cast<double*>(acc);                 // (sum, sum of squares) interleaved per angle, like (t, q)
 
         auto sweep = [&](auto plain_tag) {
             constexpr bool PLAIN = decltype(plain_tag)::value;
             unsigned* hrow = hist_blk;                       // histogram row of the next histogrammed angle
-            unsigned pend_pa = 0u, pend_pb = 0u;             // pending (matched, not yet committed) histogram update
-            int pend_ba = 0, pend_bb = 0;
-            double ra1 = 0.0, rb1 = 0.0, ra2 = 0.0, rb2 = 0.0;   // running column sums of the half-tile being reduced (two chains each)
+            double ra = 0.0, rb = 0.0;                        // running column sum of the half-tile being reduced (two chains)
             auto finish_half = [&](int angle_base, bool keep) {
-                double s1 = ra1 + rb1, s2 = ra2 + rb2;
-                s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+                double s1 = ra + rb;
                 s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-                if (keep && q4 == 0) {
-                    double2 a = acc[angle_base + c8];
-                    a.x += s1; a.y += s2;
-                    acc[angle_base + c8] = a;
-                }
-                ra1 = rb1 = ra2 = rb2 = 0.0;
+                if (keep && rh == 0) acc_d[2 * angle_base + c16] += s1;
+                ra = rb = 0.0;
             };
             for (int c = 0; c < n_chunks; ++c) {
                 const int i0 = c * kChunk;
@@ -304,26 +294,14 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
                         jb = invalid[1] ? j_fill[1] : jb;
                     }
                     (kk < 8 ? my0 : my1)[kk & 7] = make_double2(ja + jb, fma(jb, jb, ja * ja));   // columns >= A are never read back
-                    {   // one row of the other half-tile (chunk c-1's angles 8-15 during steps 0-7, this chunk's 0-7 during 8-15)
-                        const double2 v = (kk < 8 ? col1 : col0)[(kk & 7) * kHalfPitch];
-                        if (kk & 1) { rb1 += v.x; rb2 += v.y; } else { ra1 += v.x; ra2 += v.y; }
+                    {   // two rows of the other half-tile (chunk c-1's angles 8-15 during steps 0-7, this chunk's 0-7 during 8-15)
+                        const double* cc = (kk < 8 ? col1 : col0) + (2 * (kk & 7)) * (2 * kHalfPitch);
+                        ra += cc[0];
+                        rb += cc[2 * kHalfPitch];
                     }
-                    if (HS > 0) {          // compile-time stride: match at the histogrammed angle, commit a few steps later
-                        constexpr int kLag = (HS > HPEM_HIST_LAG ? HPEM_HIST_LAG : HS - 1);
-                        if (kk % (HS > 0 ? HS : 1) == 0 && i0 + kk < A) {
-                            pend_pa = hist_bin_match(ja, PLAIN || row_ok[0], h_shift, h_lo_key, h_last, pend_ba);
-                            pend_pb = hist_bin_match(jb, PLAIN || row_ok[1], h_shift, h_lo_key, h_last, pend_bb);
-                        }
-                        if (kk % (HS > 0 ? HS : 1) == kLag && i0 + kk - kLag < A) {
-                            hist_commit(hrow, pend_ba, pend_pa, lanemask_lt);
-                            hist_commit(hrow, pend_bb, pend_pb, lanemask_lt);
-                            hrow += m.n_bins;
-                        }
-                    } else if (HS < 0 && ((i0 + kk) & h_mask) == 0 && i0 + kk < A) {
-                        pend_pa = hist_bin_match(ja, PLAIN || row_ok[0], h_shift, h_lo_key, h_last, pend_ba);
-                        pend_pb = hist_bin_match(jb, PLAIN || row_ok[1], h_shift, h_lo_key, h_last, pend_bb);
-                        hist_commit(hrow, pend_ba, pend_pa, lanemask_lt);
-                        hist_commit(hrow, pend_bb, pend_pb, lanemask_lt);
+                    if (HS != 0 && (HS > 0 ? (kk % (HS > 0 ? HS : 1) == 0) : (((i0 + kk) & h_mask) == 0)) && i0 + kk < A) {
+                        hist_add(hrow, ja, PLAIN || row_ok[0], h_shift, h_lo_key, h_last);
+                        hist_add(hrow, jb, PLAIN || row_ok[1], h_shift, h_lo_key, h_last);
                         hrow += m.n_bins;
                     }
                     e1a *= r1a; r1a *= b1[0].q;
@@ -344,10 +322,9 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
             }
             // the last chunk's upper half has no sweep to hide behind
 #pragma unroll
-            for (int rr = 0; rr < 8; rr += 2) {
-                const double2 va = col1[rr * kHalfPitch], vb = col1[(rr + 1) * kHalfPitch];
-                ra1 += va.x; ra2 += va.y;
-                rb1 += vb.x; rb2 += vb.y;
+            for (int rr = 0; rr < 16; rr += 2) {
+                ra += col1[rr * (2 * kHalfPitch)];
+                rb += col1[(rr + 1) * (2 * kHalfPitch)];
             }
             finish_half((n_chunks - 1) * kChunk + 8, true);
         };
