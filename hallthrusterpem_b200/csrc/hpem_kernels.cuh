@@ -212,11 +212,12 @@ __device__ __forceinline__ double beam_init_offset(BeamState& b, double h, doubl
     b.gc = (o == 0) ? g0 : (o == 1) ? g0 * b.qk : (o == 2) ? g0 * (b.qk * b.qk) : g0 * (b.qk * b.qk * b.qk);
     return u;
 }
+template <bool FAST = false>
 __device__ __forceinline__ void beam_restart(BeamState& b, int i0) {  // exact values at angle index i0
     const double di = double(i0);
-    b.ec = exp(-b.x * (di * di));
-    b.rc = exp(-b.x * (2.0 * di + 1.0));
-    b.gc = exp(-b.x * (2.0 * kChunk * di + double(kChunk * kChunk)));
+    b.ec = m_exp<FAST>(-b.x * (di * di));
+    b.rc = m_exp<FAST>(-b.x * (2.0 * di + 1.0));
+    b.gc = m_exp<FAST>(-b.x * (2.0 * kChunk * di + double(kChunk * kChunk)));
 }
 __device__ __forceinline__ void beam_next_chunk(BeamState& b) {
     b.ec *= b.gc;
@@ -397,8 +398,13 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
         for (int c = 0; c < n_chunks; ++c) {
             const int i0 = c * kChunk;
             if (c != 0 && (c % kRestartChunks) == 0) {  // exact restart bounds the recurrence error for large A
-                beam_restart(b1, i0 + off);
-                beam_restart(b2, i0 + off);
+                if (fast) {                             // same back end as the prologue (and as K2: its rows match K1u's bit for bit)
+                    beam_restart<true>(b1, i0 + off);
+                    beam_restart<true>(b2, i0 + off);
+                } else {
+                    beam_restart<false>(b1, i0 + off);
+                    beam_restart<false>(b2, i0 + off);
+                }
             }
             double e1 = b1.amp * b1.ec, e2 = b2.amp * b2.ec;
             double r1 = b1.rc, r2 = b2.rc;

@@ -72,11 +72,12 @@ __device__ __forceinline__ void sweep_beam_init(SweepBeam& b, double& x, double 
     b.hh = b.gc * b.gc;
     b.ec = 1.0;
 }
+template <bool FAST = false>
 __device__ __forceinline__ void sweep_beam_restart(SweepBeam& b, double x, int i0) {
     const double di = double(i0);
-    b.ec = exp(-x * (di * di));
-    b.rc = exp(-x * (2.0 * di + 1.0));
-    b.gc = exp(-x * (2.0 * kChunk * di + double(kChunk * kChunk)));
+    b.ec = m_exp<FAST>(-x * (di * di));
+    b.rc = m_exp<FAST>(-x * (2.0 * di + 1.0));
+    b.gc = m_exp<FAST>(-x * (2.0 * kChunk * di + double(kChunk * kChunk)));
 }
 __device__ __forceinline__ void sweep_beam_next(SweepBeam& b) {
     b.ec *= b.gc;
@@ -270,11 +271,19 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
             for (int c = 0; c < n_chunks; ++c) {
                 const int i0 = c * kChunk;
                 if (RESTART && c != 0 && (c % kRestartChunks) == 0) {
+                    if (fast) {      // all 64 samples nominal: twelve branch-free exps as one block (neutralised rows have x = 0: exp(0) = 1)
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        if (row_ok[u]) {
-                            sweep_beam_restart(b1[u], bx1[u], i0);
-                            sweep_beam_restart(b2[u], bx2[u], i0);
+                        for (int u = 0; u < 2; ++u) {
+                            sweep_beam_restart<true>(b1[u], bx1[u], i0);
+                            sweep_beam_restart<true>(b2[u], bx2[u], i0);
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (row_ok[u]) {
+                                sweep_beam_restart(b1[u], bx1[u], i0);
+                                sweep_beam_restart(b2[u], bx2[u], i0);
+                            }
                         }
                     }
                 }
