@@ -238,10 +238,15 @@ class SVD:
         if not batch.on_device:
             if not torch.cuda.is_available():
                 raise RuntimeError('hallthrusterpem_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+            from .engine import device_to_host, host_to_device
             dev = torch.cuda.current_device() if self.device is None else int(self.device)
-            moved = {k: (torch.as_tensor(np.asarray(inputs[k], dtype=np.float64), device=f'cuda:{dev}')
-                         if np.ndim(inputs[k]) > 0 else inputs[k]) for k in _lib.PLUME_INPUTS}
-            return self.compress_inputs(moved, sweep_radius=sweep_radius, torr=torr).cpu().numpy()
+            shape = batch.out_shape
+            moved = host_to_device({k: (np.ascontiguousarray(np.broadcast_to(np.asarray(inputs[k], dtype=np.float64), shape))
+                                        if np.ndim(inputs[k]) > 0 else inputs[k]) for k in _lib.PLUME_INPUTS}, dev)
+            if not any(hasattr(v, 'data_ptr') for v in moved.values()):          # all scalars: one sample
+                moved['P_b'] = torch.full(shape, float(moved['P_b']), dtype=torch.float64, device=f'cuda:{dev}')
+            with torch.cuda.device(dev):
+                return device_to_host(self.compress_inputs(moved, sweep_radius=sweep_radius, torr=torr))
         dev = batch.device_index
         grid = get_grid(dev, self.dof, np.atleast_1d(np.float64(sweep_radius)))
         z = torch.empty(batch.out_shape + (self.rank,), dtype=torch.float64, device=f'cuda:{dev}')

@@ -106,7 +106,7 @@ def jion_log_likelihood(inputs: dict, meas: JionMeasurements, *, torr: float | N
     flat = {k: (np.ascontiguousarray(np.broadcast_to(v, shape)).reshape(-1) if v.size > 1 else v.reshape(-1)) for k, v in host.items()}
     ll = np.empty(n)
     pred = np.empty((n, meas.m)) if return_pred else None
-    from .engine import _thread_pool
+    from .engine import _thread_pool, device_to_host, host_to_device
     from .synthetic import shard_bounds
     devs = meas.devices if n >= 64 * len(meas.devices) else meas.devices[:1]
 
@@ -116,16 +116,15 @@ def jion_log_likelihood(inputs: dict, meas: JionMeasurements, *, torr: float | N
             return
         d = devs[r]
         with torch.cuda.device(d):
-            part = {k: (torch.as_tensor(v[lo:hi]).to(f'cuda:{d}', non_blocking=True) if v.size > 1 else float(v[0]))
-                    for k, v in flat.items()}
+            part = host_to_device({k: (v[lo:hi] if v.size > 1 else v) for k, v in flat.items()}, d)
             if not any(_is_torch(v) for v in part.values()):      # all scalars: one sample
                 part['P_b'] = torch.full((hi - lo,), float(flat['P_b'][0]), dtype=torch.float64, device=f'cuda:{d}')
             res = _loglike_on_device(_Batch(part, _lib.PLUME_INPUTS), meas, d, torr, return_pred)
             if return_pred:
-                ll[lo:hi] = res[0].cpu().numpy()
-                pred[lo:hi] = res[1].cpu().numpy()
+                ll[lo:hi] = device_to_host(res[0])
+                pred[lo:hi] = device_to_host(res[1])
             else:
-                ll[lo:hi] = res.cpu().numpy()
+                ll[lo:hi] = device_to_host(res)
 
     if len(devs) == 1:
         one(0)

@@ -24,7 +24,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from .engine import _Batch, get_grid, resolve_devices, torr_2_pa
+from .engine import _Batch, get_grid, host_to_device, resolve_devices, torr_2_pa
 
 N_SCALARS = 12
 N_MINMAX = 6
@@ -302,9 +302,7 @@ class MonteCarloMoments:
             if hi <= lo:
                 continue
             with torch.cuda.device(c.device):
-                part = {k: (torch.as_tensor(np.ascontiguousarray(a.reshape(-1)[lo:hi])).to(f'cuda:{c.device}', non_blocking=True)
-                            if a.size > 1 else float(a.reshape(-1)[0])) for k, a in arrays.items()}
-                c.accumulate(part)
+                c.accumulate(host_to_device({k: (a.reshape(-1)[lo:hi] if a.size > 1 else a) for k, a in arrays.items()}, c.device))
         return n
 
     def _gather_children(self) -> None:
