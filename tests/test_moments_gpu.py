@@ -133,3 +133,14 @@ def test_multi_device_reducer_matches_single_device(cuda_device):
     assert np.array_equal(a.sums[:3], b.sums[:3]) and np.array_equal(a.sums[L.off_hist:], b.sums[L.off_hist:])
     np.testing.assert_allclose(a.sums[:L.off_hist], b.sums[:L.off_hist], rtol=1e-12)
     assert np.array_equal(a.minmax, b.minmax)
+    # host arrays split over the devices (pinned, threaded staging) == the same arrays on one device
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    host = spt100_batch(100_000, 21)
+    one2 = MonteCarloMoments(n_angles=91, hist=HistogramSpec(), device=0, torr=133.322, scalar_shift=(30.0, 0.8, 0.05))
+    one2.accumulate({k: torch.as_tensor(v, device='cuda:0') for k, v in host.items()})
+    many2 = MonteCarloMoments(n_angles=91, hist=HistogramSpec(), devices='all', torr=133.322, scalar_shift=(30.0, 0.8, 0.05))
+    many2.accumulate(host)
+    c, d = one2.result(), many2.result()
+    L2 = one2.layout
+    assert np.array_equal(c.sums[:3], d.sums[:3]) and np.array_equal(c.sums[L2.off_hist:], d.sums[L2.off_hist:])
+    np.testing.assert_allclose(c.sums[:L2.off_hist], d.sums[:L2.off_hist], rtol=1e-12)

@@ -6,8 +6,8 @@
         tools/run_mc.py --samples 1e9 --angles 512 [--weak]                # samples sharded over the ranks
 
 Inputs are drawn on the fly by the on-device sampler (global sample index space, shard-invariant), each rank
-accumulates its contiguous index range in chunks, and ONE all-reduce(SUM) + ONE all-reduce(MAX) merge the packed
-moments (NCCL).  Rank 0 prints a JSON line with throughput (device-timed, max over ranks) and a few statistics.
+accumulates its contiguous index range in chunks, and ONE all-gather of the packed moments + a fixed-rank-order merge
+kernel combine the ranks (NCCL).  Rank 0 prints a JSON line with throughput (device-timed, max over ranks) and a few statistics.
 """
 import argparse
 import json
@@ -73,7 +73,7 @@ def main():
             'workload': f'reduce-only MC, {n_total} samples x {args.angles} angles, sampled on device, {world} GPU(s)',
             'value': n_total * args.angles / (total_ms * 1e-3), 'unit': 'evals/s', 'n_gpus': world, 'ms_total': total_ms,
             'ms_allreduce': merge_ms, 'wall_s': wall, 'launches_rank0': int(_lib.load().hpem_launch_count() - launches0),
-            'allreduce_bytes': int(mc.sums.numel() * 8 + 48), 'n_samples': res.n_samples, 'n_invalid': res.n_invalid,
+            'allreduce_bytes': int(mc.packed.numel() * 8), 'n_samples': res.n_samples, 'n_invalid': res.n_invalid,
             'V_cc': res.scalar('V_cc'), 'div_angle': res.scalar('div_angle'), 'T_c': res.scalar('T_c'),
             'j_mean_0_mid_end': [float(res.j_mean[0]), float(res.j_mean[args.angles // 2]), float(res.j_mean[-1])],
             'j_p5_p50_p95_at_angle0': [float(p[0, 0]), float(p[1, 0]), float(p[2, 0])],
