@@ -16,7 +16,10 @@ GOLDEN = sorted((Path(__file__).parent / 'golden').glob('*.npz'))
 # kernel variants: default (K1u with (n, A) / quad-row tensor stores, whole-row mode for small odd A), K1v (four lanes per
 # sample), K1u with plain stores, the pre-quad fallbacks, K1d (reference operation order)
 MODES = {'default': {}, 'no_quad': {'no_quad': True}, 'lanes4': {'lanes4': True}, 'lanes4_stg': {'lanes4': True, 'no_tma': True},
-         'lanes1': {'lanes1': True}, 'lanes1_stg': {'lanes1': True, 'no_tma': True}, 'direct': {'direct': True}}
+         'lanes1': {'lanes1': True}, 'lanes1_stg': {'lanes1': True, 'no_tma': True}, 'direct': {'direct': True},
+         # the libdevice back end of the per-sample part for EVERY warp (the default takes the branch-free functions of
+         # csrc/hpem_fastmath.cuh for warps whose samples are all in the nominal range): both must meet the same rules
+         'no_fastmath': {'no_fastmath': True}}
 
 
 def _models():
@@ -66,6 +69,24 @@ def test_golden_device_path(path, cuda_device):
     assert out['j_ion'].is_cuda and out['j_ion'].dtype == torch.float64
     host = {k: (v.cpu().numpy() if hasattr(v, 'cpu') else v) for k, v in out.items()}
     _compare(host, g, inputs, meta['torr_2_pa'], g['sweep_radius'], path.stem + ':device')
+
+
+def test_device_all_on_any_box_and_back_ends_agree(cuda_device):
+    """`device='all'` works whatever the number of visible GPUs (bit-identical to device 0), and the two arithmetic back ends
+    of the per-sample part agree far inside the parity tolerance (they differ in last bits only)."""
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    _, _, plume_cathode = _models()
+    b = spt100_batch(20_000, 404)
+    one = plume_cathode(b, 1.0, n_angles=91, device=0, extras=True)
+    many = plume_cathode(b, 1.0, n_angles=91, device='all', extras=True)
+    for k in ('V_cc', 'j_ion', 'div_angle', 'T_c', 'cos_div', 'invalid'):
+        assert np.array_equal(one[k], many[k]), k
+    slow = plume_cathode(b, 1.0, n_angles=91, device=0, extras=True, no_fastmath=True)
+    floor = 2 * np.finfo(float).eps * b['I_B0'][:, None] / (2 * np.pi)      # one ulp of `decay` (both back ends share it)
+    assert np.all(np.abs(one['j_ion'] - slow['j_ion']) <= 2e-13 * np.abs(slow['j_ion']) + floor)
+    assert np.all(np.abs(one['cos_div'] - slow['cos_div']) <= 1e-13 * np.abs(slow['cos_div']))
+    assert np.all(np.abs(one['V_cc'] - slow['V_cc']) <= 1e-13 * np.maximum(np.abs(slow['V_cc']), 1.0))
+    assert np.array_equal(one['invalid'], slow['invalid'])
 
 
 def test_separate_functions_match_fused(cuda_device):
