@@ -26,7 +26,7 @@ CATHODE_INPUTS = INPUT_NAMES[:6]
 PLUME_INPUTS = ('P_b',) + INPUT_NAMES[6:14]
 
 HPEM_OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 FLAG_FORCE_DIRECT = 1
 FLAG_NO_TMA = 2
 FLAG_LANES1 = 4
@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = (
     'hpem_abi_version', 'hpem_source_hash', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',
     'hpem_eval', 'hpem_eval_host', 'hpem_launch_count',
     'hpem_moments_layout_query', 'hpem_moments_accumulate', 'hpem_sample_inputs', 'hpem_moments_accumulate_sampled',
-    'hpem_moments_merge',
+    'hpem_moments_merge', 'hpem_quadrature_table_eval',
     'hpem_measurements_create', 'hpem_measurements_destroy', 'hpem_loglike', 'hpem_logsumexp',
     'hpem_basis_create', 'hpem_basis_destroy', 'hpem_compress', 'hpem_compress_field', 'hpem_reconstruct',
 )
@@ -199,6 +199,8 @@ def load() -> ctypes.CDLL:
         lib.hpem_moments_accumulate.restype = i32
         lib.hpem_moments_merge.argtypes = [i32, ctypes.POINTER(HpemMomentsLayout), i32, vp, i64, vp, vp, vp]
         lib.hpem_moments_merge.restype = i32
+        lib.hpem_quadrature_table_eval.argtypes = [i32, dptr, dptr, i64, dptr, dptr, dptr]
+        lib.hpem_quadrature_table_eval.restype = i32
         u64 = ctypes.c_uint64
         lib.hpem_sample_inputs.argtypes = [i32, i64, u64, u64, ctypes.POINTER(HpemPrior), ctypes.POINTER(vp), vp]
         lib.hpem_sample_inputs.restype = i32

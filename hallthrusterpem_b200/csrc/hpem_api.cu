@@ -79,6 +79,8 @@ struct Workspace {
     unsigned* d_hist_partials = nullptr;   // K2 per-block histograms; all-zero between calls (the finalize kernel re-zeroes them)
     size_t hist_partials_cap = 0;
     cudaEvent_t moments_done = nullptr;    // end of the last reduce-only pass that used the scratch buffers above
+    double* d_qtable = nullptr;            // K2: tabulated Simpson sums N_d(x), N_n(x) of this grid (hpem_qtable.cuh), built on first use
+    int qt_key_lo = 0, qt_bins = 0;
 };
 
 }  // namespace
@@ -92,6 +94,7 @@ struct hpem_grid {
     double* d_alpha = nullptr;
     double* d_radii = nullptr;
     std::vector<double> alpha_host;
+    std::vector<double2> w_host;   // fused weights (wd_i, wn_i), zero-padded
     size_t smem_tma = 0, smem_tma32 = 0, smem_tma1 = 0, smem_quad = 0, smem_quad1 = 0, smem_stg = 0, smem_nostore = 0, smem_rows = 0;  // dynamic shared memory of the K1u variants
     size_t smem_v_store = 0, smem_v_nostore = 0;          // ... and of K1v
     int sm_count = 148;
@@ -456,6 +459,7 @@ int hpem_grid_create(int device, int n_angles, const double* alpha, const double
         if (e_ != cudaSuccess)                                                                               \
             return cleanup(fail(HPEM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)));             \
     } while (0)
+    g->w_host = w;
     HPEM_CUDA_G(cudaMalloc((void**)&g->d_w, w.size() * sizeof(double2)));
     HPEM_CUDA_G(cudaMalloc((void**)&g->d_alpha, n_angles * sizeof(double)));
     HPEM_CUDA_G(cudaMalloc((void**)&g->d_radii, n_radii * sizeof(double)));
@@ -514,6 +518,7 @@ int hpem_grid_destroy(hpem_grid* g) {
     if (ws.d_partials) cudaFree(ws.d_partials);
     if (ws.d_partial_minmax) cudaFree(ws.d_partial_minmax);
     if (ws.d_hist_partials) cudaFree(ws.d_hist_partials);
+    if (ws.d_qtable) cudaFree(ws.d_qtable);
     if (ws.moments_done) cudaEventDestroy(ws.moments_done);
     for (auto e : ws.events) cudaEventDestroy(e);
     for (auto e : ws.h2d_events) cudaEventDestroy(e);
@@ -872,6 +877,18 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
         HPEM_CUDA(cudaMemsetAsync(ws.d_hist_partials, 0, ws.hist_partials_cap * sizeof(unsigned), st));
     }
 
+    if (!ws.d_qtable) {     // the grid's quadrature table: built once (host, long double), kept with the handle
+        std::vector<double> wd(g->n_angles), wn(g->n_angles), rows;
+        for (int i = 0; i < g->n_angles; ++i) {
+            wd[i] = g->w_host[i].x;
+            wn[i] = g->w_host[i].y;
+        }
+        qtable_build(g->n_angles, wd.data(), wn.data(), rows, ws.qt_key_lo, ws.qt_bins);
+        HPEM_CUDA(cudaMalloc((void**)&ws.d_qtable, rows.size() * sizeof(double)));
+        HPEM_CUDA(cudaMemcpyAsync(ws.d_qtable, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        HPEM_CUDA(cudaStreamSynchronize(st));   // `rows` is pageable and dies with this scope
+    }
+
     hpem_outputs no_out = {};
     hpem_inputs no_in = {};
     EvalParams p;
@@ -879,6 +896,12 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
     p.has_thrust = spec->want_thrust != 0;
     MomentsParams m;
     fill_moments_params(*spec, lay, m);
+    static const int no_qtable_env = []() { const char* v = std::getenv("HPEM_NO_QTABLE"); return v ? std::atoi(v) : 0; }();
+    m.qt.rows = no_qtable_env ? nullptr : ws.d_qtable;
+    m.qt.key_lo = ws.qt_key_lo;
+    m.qt.n_bins = ws.qt_bins;
+    m.qt.wd0 = g->w_host[0].x;
+    m.qt.wn0 = g->w_host[0].y;
     m.partials = ws.d_partials;
     m.partial_minmax = ws.d_partial_minmax;
     m.hist_partials = ws.d_hist_partials;
@@ -905,6 +928,19 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
     HPEM_CUDA(cudaGetLastError());
     HPEM_CUDA(cudaEventRecord(ws.moments_done, st));
     g_launches.fetch_add(3, std::memory_order_relaxed);
+    return HPEM_OK;
+}
+
+int hpem_quadrature_table_eval(int n_angles, const double* wd, const double* wn, int64_t n_x, const double* x, double* nd, double* nn) {
+    if (n_angles < 2 || n_angles > 8192) return fail(HPEM_ERR_INVALID_ARG, "n_angles must be in [2, 8192], got %d", n_angles);
+    if (!wd || !wn || n_x < 0 || (n_x > 0 && (!x || !nd || !nn))) return fail(HPEM_ERR_INVALID_ARG, "NULL argument");
+    std::vector<double> rows;
+    hpem::QTableRef q;
+    hpem::qtable_build(n_angles, wd, wn, rows, q.key_lo, q.n_bins);
+    q.rows = rows.data();
+    q.wd0 = wd[0];
+    q.wn0 = wn[0];
+    for (int64_t k = 0; k < n_x; ++k) hpem::qtable_eval(q, x[k], std::exp(-x[k]), nd[k], nn[k]);
     return HPEM_OK;
 }
 

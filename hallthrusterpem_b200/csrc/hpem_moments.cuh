@@ -24,6 +24,7 @@
 // comes from E[x^2] - E[x]^2.  The per-sample scalars are accumulated about a caller-supplied shift.
 #pragma once
 #include "hpem_kernels.cuh"
+#include "hpem_qtable.cuh"
 
 namespace hpem {
 
@@ -40,6 +41,7 @@ struct MomentsParams {
     double* partials;     // [gridDim.x][n_part]   n_part = kMomScalars + 2 A   (raw sums of one block)
     double* partial_minmax;  // [gridDim.x][6]  (-min, max) x (V_cc, div_angle, T_c)
     unsigned* hist_partials; // [gridDim.x][n_hist_angles][n_bins]   zero on entry, re-zeroed by the finalize kernel
+    QTableRef qt;         // tabulated Simpson sums of the grid (rows == nullptr: accumulate them angle by angle)
 };
 constexpr int kMomScalars = 12;  // n_samples n_invalid n_nonfinite_rows | {n_finite sum M2} x {V_cc div_angle T_c}
 #ifndef HPEM_THREADS_M
@@ -162,6 +164,8 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
         SweepBeam b1[2], b2[2];
         double bx1[2], bx2[2], bamp1[2], bamp2[2];     // recurrence exponents / amplitudes (restarts, row checks)
         double v_cc[2] = {0.0, 0.0}, j_cex[2], a1v[2];
+        double num[2] = {0.0, 0.0}, den[2] = {0.0, 0.0};   // the Simpson sums of plume.py:121-122
+        const bool use_qt = m.qt.rows != nullptr;
         auto prologue = [&](auto fast_tag) {
             constexpr bool FAST = decltype(fast_tag)::value;
 #pragma unroll
@@ -181,6 +185,13 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
                 bamp2[u] = __dmul_rn(base, k.amp2);
                 sweep_beam_init<FAST>(b1[u], bx1[u], p.h, k.a1);
                 sweep_beam_init<FAST>(b2[u], bx2[u], p.h, k.a2);
+                if (FAST && use_qt) {   // both sums from the grid's table: amplitude x N(x) per beam (hpem_qtable.cuh)
+                    double nd1, nn1, nd2, nn2;
+                    qtable_eval(m.qt, bx1[u], b1[u].rc, nd1, nn1);
+                    qtable_eval(m.qt, bx2[u], b2[u].rc, nd2, nn2);
+                    den[u] = fma(bamp1[u], nd1, bamp2[u] * nd2);
+                    num[u] = fma(bamp1[u], nn1, bamp2[u] * nn2);
+                }
             }
         };
         const bool nominal = prologue_nominal(x_in[0], p.torr, want_cathode, true, p.radius0) &&
@@ -192,7 +203,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
             prologue(std::false_type{});
 
         bool invalid[2], row_ok[2];
-        double thrust[2], num[2] = {0.0, 0.0}, den[2] = {0.0, 0.0}, j_fill[2];
+        double thrust[2], j_fill[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             thrust[u] = x_in[u][IN_T];
@@ -258,6 +269,10 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
         const double* col1 = col0 + 32 * (2 * kHalfPitch);
         double* acc_d = reinterpret_cast<double*>(acc);                 // (sum, sum of squares) interleaved per angle, like (t, q)
 
+        // PLAIN warps (all rows ordinary) of the fast back end already hold the two Simpson sums (table); every other warp
+        // accumulates them angle by angle and selects the fill value per element
+        const bool tabulated = plain && fast && use_qt;
+        if (!tabulated) den[0] = den[1] = num[0] = num[1] = 0.0;
         auto sweep = [&](auto plain_tag) {
             constexpr bool PLAIN = decltype(plain_tag)::value;
             unsigned* hrow = hist_blk;                       // histogram row of the next histogrammed angle
@@ -291,12 +306,14 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
                 double e1b = bamp1[1] * b1[1].ec, e2b = bamp2[1] * b2[1].ec, r1b = b1[1].rc, r2b = b2[1].rc;
 #pragma unroll
                 for (int kk = 0; kk < kChunk; ++kk) {
-                    const double2 w = wsm[i0 + kk];          // zero beyond A
                     const double sa = e1a + e2a, sb = e1b + e2b;   // j_beam + j_scat
-                    den[0] = fma(w.x, sa, den[0]);
-                    num[0] = fma(w.y, sa, num[0]);
-                    den[1] = fma(w.x, sb, den[1]);
-                    num[1] = fma(w.y, sb, num[1]);
+                    if (!PLAIN) {
+                        const double2 w = wsm[i0 + kk];      // zero beyond A
+                        den[0] = fma(w.x, sa, den[0]);
+                        num[0] = fma(w.y, sa, num[0]);
+                        den[1] = fma(w.x, sb, den[1]);
+                        num[1] = fma(w.y, sb, num[1]);
+                    }
                     double ja = sa + j_cex[0], jb = sb + j_cex[1];  // the values current_density() returns (plume.py:102)
                     if (!PLAIN) {
                         ja = invalid[0] ? j_fill[0] : ja;
@@ -337,7 +354,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
             }
             finish_half((n_chunks - 1) * kChunk + 8, true);
         };
-        if (plain)
+        if (tabulated)
             sweep(std::true_type{});
         else
             sweep(std::false_type{});

@@ -7,6 +7,7 @@
 // shards of one global index range reproduce the unsharded run bit for bit.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #include "hpem_device.cuh"
 
@@ -47,7 +48,7 @@ __host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// two uniforms in [0, 1) with 53 random bits each, for (sample, pair) -- pair p serves inputs 2p and 2p+1
+// two uniforms in [0, 1) with 53 random bits each for (sample, pair, stream): the second stream of the Normal prior
 __host__ __device__ inline void uniform_pair(unsigned long long seed, unsigned long long sample, uint32_t pair, uint32_t stream,
                                              double& u0, double& u1) {
     uint32_t o[4];
@@ -65,6 +66,30 @@ __host__ __device__ inline void uniform_pair(unsigned long long seed, unsigned l
     u0 = (double)(a >> 11) * 0x1.0p-53;
     u1 = (double)(b >> 11) * 0x1.0p-53;
 #endif
+}
+
+// Three uniforms in [0, 1) with 42 random bits each from ONE Philox call, for (sample, triple) -- triple t serves inputs
+// 3t, 3t+1, 3t+2, so the 15 inputs of a sample cost five calls.  Uniform j is k_j 2^-42 with the 42-bit integer
+// k_j = (bits 10j..10j+9 of word 3) << 32 | word j.  k_j << 10 is dropped into the mantissa of 1.0 (two integer
+// operations per word), and ONE exact subtraction gives u; the affine map of the prior is then the usual fma(u, b - a, a),
+// which keeps every draw inside [a, b).  (The first version took two 53-bit uniforms per call: eight calls per sample and
+// five fp64 operations per uniform, a quarter of the reduce-only kernel's per-sample work.)
+__host__ __device__ inline void uniform_triple(unsigned long long seed, unsigned long long sample, uint32_t triple, double (&u)[3]) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), triple, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const uint32_t top = j == 0 ? (o[3] << 10) : (j == 1 ? o[3] : (o[3] >> 10));   // 10 bits of word 3 at bits 10..19
+        const uint32_t hi = 0x3FF00000u | (top & 0x000FFC00u) | (o[j] >> 22), lo = o[j] << 10;
+#if defined(__CUDA_ARCH__)
+        u[j] = __hiloint2double((int)hi, (int)lo) - 1.0;
+#else
+        const uint64_t bits = ((uint64_t)hi << 32) | lo;
+        double d;
+        memcpy(&d, &bits, sizeof(d));
+        u[j] = d - 1.0;
+#endif
+    }
 }
 
 // Normal(mean a, std b): Box-Muller with a second uniform from stream 1 of the same (sample, input).  Out of line: no prior
@@ -87,17 +112,23 @@ __device__ __forceinline__ double apply_prior(const Prior& pr, double u, unsigne
     }
 }
 
-// All 15 inputs of N samples (N = 1, or the two samples a thread of the reduce-only kernel owns).  The 8 N Philox calls come
+// All 15 inputs of N samples (N = 1, or the two samples a thread of the reduce-only kernel owns).  The 5 N Philox calls come
 // first, in ONE basic block, so their ten-round dependency chains interleave; then the affine maps; the exponentials of
 // the LogUniform inputs (and the rare Normal inputs) last, behind warp-uniform tests of the prior masks.  Values are
 // exactly those of apply_prior() applied input by input.
 template <int N>
 __device__ __forceinline__ void sample_inputs_n(const SamplerParams& sp, const unsigned long long (&local_index)[N], double (&x)[N][15]) {
-    double u[N][16];
+    double u[N][15];
 #pragma unroll
-    for (uint32_t pair = 0; pair < 8; ++pair) {
+    for (uint32_t t = 0; t < 5; ++t) {
 #pragma unroll
-        for (int s = 0; s < N; ++s) uniform_pair(sp.seed, sp.first_index + local_index[s], pair, 0u, u[s][2 * pair], u[s][2 * pair + 1]);
+        for (int s = 0; s < N; ++s) {
+            double v[3];
+            uniform_triple(sp.seed, sp.first_index + local_index[s], t, v);
+            u[s][3 * t] = v[0];
+            u[s][3 * t + 1] = v[1];
+            u[s][3 * t + 2] = v[2];
+        }
     }
 #pragma unroll
     for (int k = 0; k < 15; ++k) {

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HPEM_ABI_VERSION 2
+#define HPEM_ABI_VERSION 3
 
 /* status codes */
 #define HPEM_OK 0
@@ -178,6 +178,14 @@ int hpem_moments_layout_query(const hpem_grid *grid, const hpem_moments_spec *sp
 /* DEVICE buffers, asynchronous on `stream`.  `sums` (layout.n_sums doubles) and `minmax` (6 doubles) are updated. */
 int hpem_moments_accumulate(hpem_grid *grid, int64_t n, const hpem_inputs *in, double torr_2_pa,
                             const hpem_moments_spec *spec, double *sums, double *minmax, void *stream);
+
+/* The Simpson sums of a Gaussian profile on the uniform grid (plume.py:117-123 with the fused weights above) as tabulated
+ * functions of x = (h / alpha_beam)^2:  N_d(x) = sum_i wd[i] exp(-x i^2),  N_n(x) = sum_i wn[i] exp(-x i^2).  The reduce-only
+ * pass uses this table (csrc/hpem_qtable.cuh) instead of accumulating the two sums angle by angle.  This entry point
+ * evaluates it ON THE HOST with the arithmetic the kernel uses (no device needed), so the table can be checked against
+ * direct sums anywhere: nd[k], nn[k] for x[k], k < n_x. */
+int hpem_quadrature_table_eval(int n_angles, const double *wd, const double *wn, int64_t n_x, const double *x,
+                               double *nd, double *nn);
 
 /* Merge n_parts packed vectors, part r = [sums (layout.n_sums) | minmax (6)] at parts + r * part_stride (DEVICE memory),
  * in index order into sums / minmax (DEVICE, overwritten; must not alias parts).  Every rank runs this on the all-gathered

@@ -1,7 +1,7 @@
 """NumPy statement of the on-device sampler's stream (TEST INFRASTRUCTURE ONLY; never imported by the product package).
 
-Philox4x32-10 (Salmon et al., SC'11), counter = (sample index lo, hi, input pair, stream), key = seed; two 53-bit uniforms
-per call; Uniform / LogUniform / const transforms as in csrc/hpem_sampler.cuh.  The Random123 known-answer vectors pin
+Philox4x32-10 (Salmon et al., SC'11), counter = (sample index lo, hi, input triple, 0), key = seed; three 42-bit uniforms
+per call (word j plus ten bits of word 3); Uniform / LogUniform / const transforms as in csrc/hpem_sampler.cuh.  The Random123 known-answer vectors pin
 the generator in tests/test_host_cpu.py; tests/test_sampler_gpu.py compares the device draws with this statement."""
 from __future__ import annotations
 
@@ -31,16 +31,16 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def philox_uniforms(seed: int, first_index: int, n: int) -> np.ndarray:
-    """(n, 16) uniforms in [0, 1): column k is the uniform behind input k (column 15 is unused)."""
+    """(n, 15) uniforms in [0, 1): column k is the uniform behind input k.  Call t of a sample serves inputs 3t..3t+2;
+    uniform j of a call is k_j 2^-42 with k_j = (bits 10j..10j+9 of word 3) << 32 | word j."""
     idx = np.uint64(first_index) + np.arange(n, dtype=np.uint64)
     lo, hi = idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32)
-    out = np.empty((n, 16))
-    for pair in range(8):
-        o0, o1, o2, o3 = philox4x32_10(lo, hi, np.full(n, pair, np.uint64), np.zeros(n, np.uint64),
-                                       seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-        a, b = (o1 << np.uint64(32)) | o0, (o3 << np.uint64(32)) | o2
-        out[:, 2 * pair] = (a >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
-        out[:, 2 * pair + 1] = (b >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+    out = np.empty((n, 15))
+    for t in range(5):
+        o = philox4x32_10(lo, hi, np.full(n, t, np.uint64), np.zeros(n, np.uint64), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        for j in range(3):
+            k = (((o[3] >> np.uint64(10 * j)) & np.uint64(0x3FF)) << np.uint64(32)) | o[j]
+            out[:, 3 * t + j] = k.astype(np.float64) * 2.0 ** -42
     return out
 
 

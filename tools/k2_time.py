@@ -1,5 +1,6 @@
 #!/usr/bin/env python
 """Developer probe: reduce-only pass (K2) throughput.  python tools/k2_time.py [A ...]"""
+import os
 import sys
 from pathlib import Path
 
@@ -12,9 +13,10 @@ from hallthrusterpem_b200.synthetic import spt100_batch  # noqa: E402
 
 PEAK = 1.8544e13
 for A in [int(a) for a in sys.argv[1:]] or [91, 256, 512]:
-    n = 8_000_000 if A <= 256 else 4_000_000
-    for label, hist, sampled in (('sampled+hist8', HistogramSpec(angle_stride=8), True), ('sampled nohist', HistogramSpec(angle_stride=0), True),
-                                 ('arrays+hist8', HistogramSpec(angle_stride=8), False)):
+    n = int(float(os.environ.get('K2_N', 8_000_000 if A <= 256 else 4_000_000)))
+    modes = (('sampled+hist8', HistogramSpec(angle_stride=8), True), ('sampled nohist', HistogramSpec(angle_stride=0), True),
+             ('arrays+hist8', HistogramSpec(angle_stride=8), False))
+    for label, hist, sampled in modes[:int(os.environ.get('K2_MODES', 3))]:
         mc = MonteCarloMoments(n_angles=A, device=0, hist=hist)
         if sampled:
             run = lambda: mc.accumulate_sampled(n, 7, 0)   # noqa: E731
@@ -32,4 +34,5 @@ for A in [int(a) for a in sys.argv[1:]] or [91, 256, 512]:
         ms = float(np.median(ts))
         nn = n if sampled else nb
         rate = nn * A / ms * 1e3
-        print(f'K2 A={A:4d} {label:15s} n={nn:9d}  {ms:8.3f} ms  {rate / 1e9:8.1f} Geval/s  frac(10 instr/eval) {10 * rate / PEAK:.3f}', flush=True)
+        print(f'K2 A={A:4d} {label:15s} n={nn:9d}  {ms:8.3f} ms  {rate / 1e9:8.1f} Geval/s  frac(10 instr/eval) {10 * rate / PEAK:.3f}  '
+              f'{ms * 1e3 / (nn / (148 * 768)):7.2f} us/round', flush=True)

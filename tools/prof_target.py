@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """ncu target: a few launches of ONE kernel family.  python tools/prof_target.py {k1u|k1q|k2|k2s|k3|k4|k5|k1w}
 (k1u: 1e6 x 200, (n, A) tensor stores; k1q: 1e6 x 91, quad-row tensor stores; k1w: 1e5 x 91 x 25 radii)"""
+import os
 import sys
 from pathlib import Path
 
@@ -27,7 +28,7 @@ if what in ('k1u', 'k1q'):
 elif what in ('k2', 'k2s'):
     from hallthrusterpem_b200.mc import HistogramSpec, MonteCarloMoments
     n = 2_000_000
-    mc = MonteCarloMoments(n_angles=256, device=0, hist=HistogramSpec(angle_stride=8))
+    mc = MonteCarloMoments(n_angles=int(os.environ.get('K2_A', 256)), device=0, hist=HistogramSpec(angle_stride=8))
     b = dev(spt100_batch(n, 1))
     for _ in range(3):
         mc.accumulate_sampled(n, 7, 0) if what == 'k2s' else mc.accumulate(b)
