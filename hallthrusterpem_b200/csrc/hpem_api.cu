@@ -848,13 +848,14 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
     HPEM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, g->device));
     const size_t smem_budget = (size_t)dev_smem - 4096;   // static shared memory of the kernel + slack
     static const int warps_env = []() { const char* v = std::getenv("HPEM_MOMENTS_WARPS"); return v ? std::atoi(v) : 0; }();
-    int warps = warps_env > 0 ? std::min(warps_env, kMaxWarpsM) : kMaxWarpsM;
+    const bool restart = n_chunks > kRestartChunks;
+    const int max_warps = restart ? kWarpsLongM : kMaxWarpsM;      // the launch bounds of the two kernel families
+    int warps = warps_env > 0 ? std::min(warps_env, max_warps) : max_warps;
     while (warps > 1 && moments_smem_bytes(g->n_angles_pad, n_chunks * kChunk, warps) > smem_budget) --warps;
     const size_t smem = moments_smem_bytes(g->n_angles_pad, n_chunks * kChunk, warps);
     if (smem > smem_budget)
         return fail(HPEM_ERR_UNSUPPORTED, "%d angles need %zu bytes of shared memory (> %zu)", g->n_angles, smem, smem_budget);
     const int hs = spec->hist_angle_stride == 0 ? 0 : (spec->hist_angle_stride == 8 ? 8 : -1);
-    const bool restart = n_chunks > kRestartChunks;
     const int threads = warps * 32;
     const int64_t batches = (n + 2 * threads - 1) / (2 * threads);
     const int blocks = (int)std::min<int64_t>(batches, (int64_t)g->sm_count);

@@ -102,8 +102,14 @@ __device__ __forceinline__ void hist_add(unsigned* hrow, double j, bool ok, int 
 
 // HS: histogram angle stride known at compile time (8, the default), 0 = no histograms, -1 = any power-of-two stride.
 // RESTART: the row is longer than kRestartChunks chunks, the recurrences are re-anchored with exact exps (A > 256).
+// Launch geometry.  Rows of up to 256 angles: 12 warps per SM at 168 registers.  Longer rows (RESTART) run 8 warps at 250
+// registers: the restart block's twelve exponentials no longer spill into the sweep, and the smaller shared-memory
+// footprint leaves the L1 to the quadrature table (B200, 4e7 samples, histograms: 272 angles 9.5 -> 9.8e11 evals/s,
+// 512: 1.12 -> 1.20e12, 640: 1.10 -> 1.23e12; at 256 angles and below 12 warps stay 3-10 % ahead).  Registers come in
+// blocks of four warps, so 9-11 warps cannot have more than 168 either.
+constexpr int kWarpsLongM = 8;
 template <bool SAMPLED, int HS, bool RESTART>
-__global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams p, const MomentsParams m,
+__global__ void __launch_bounds__(RESTART ? kWarpsLongM * 32 : kThreadsM, 1) moments_kernel(const EvalParams p, const MomentsParams m,
                                                                const __grid_constant__ SamplerParams sp) {
     extern __shared__ __align__(16) unsigned char smem_m[];
     const int A = p.n_angles;
@@ -134,9 +140,22 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
     unsigned* hist_blk = m.hist_partials + (size_t)blockIdx.x * m.n_hist_angles * m.n_bins;
 
     const long long batch = (long long)n_warps * 64;
+    // SAMPLED: the Philox words of a batch are drawn one iteration ahead, next to the latency-bound tail of the previous
+    // batch (last column reduce, division, arccos), where the integer pipe is idle
+    uint32_t words[2][5][4];
+    auto draw_words = [&](long long w0_next) {
+        unsigned long long nidx[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long long s_raw = w0_next + u * 32 + lane;
+            nidx[u] = (unsigned long long)(s_raw < p.n ? s_raw : p.n - 1);
+        }
+        sample_words_n<2>(sp, nidx, words);
+    };
+    if (SAMPLED) draw_words((long long)blockIdx.x * batch + warp * 64);
     for (long long b0 = (long long)blockIdx.x * batch; b0 < p.n; b0 += (long long)gridDim.x * batch) {
         const long long w0 = b0 + warp * 64;
-        if (w0 >= p.n) continue;   // warp-uniform; no block-level barrier inside the loop
+        if (w0 >= p.n) continue;   // warp-uniform; no block-level barrier inside the loop (later batches of this warp are out of range too)
 
         // ---- the two samples of this thread: inputs ----
         double x_in[2][kNumInputs];
@@ -149,7 +168,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
             sidx[u] = (unsigned long long)(active[u] ? s_raw : p.n - 1);   // inactive lanes shadow the last sample, contribute nothing
         }
         if (SAMPLED) {
-            sample_inputs_n<2>(sp, sidx, x_in);
+            sample_transform_n<2>(sp, sidx, words, x_in);
         } else {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -360,14 +379,16 @@ __global__ void __launch_bounds__(kThreadsM, 1) moments_kernel(const EvalParams 
             sweep(std::false_type{});
 
         // ---- per-sample epilogue: plume.py:124-127,137 (NOT masked by `invalid`) ----
+        // The branch-free division and arccos are evaluated unconditionally, in one basic block with the draw of the next
+        // batch's Philox words; the libdevice forms replace them in the rare warps that need IEEE special cases.
+        if (SAMPLED) draw_words(w0 + (long long)gridDim.x * batch);
         double cd[2], dv[2];
-        if (fast && __all_sync(0xffffffffu, fm_mid(den[0]) && fm_mid0(num[0]) && fm_mid(den[1]) && fm_mid0(num[1]))) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                cd[u] = fm_div(num[u], den[u]);
-                dv[u] = fm_acos(cd[u]);
-            }
-        } else {
+        for (int u = 0; u < 2; ++u) {
+            cd[u] = fm_div(num[u], den[u]);
+            dv[u] = fm_acos(cd[u]);
+        }
+        if (!(fast && __all_sync(0xffffffffu, fm_mid(den[0]) && fm_mid0(num[0]) && fm_mid(den[1]) && fm_mid0(num[1])))) {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 cd[u] = num[u] / den[u];

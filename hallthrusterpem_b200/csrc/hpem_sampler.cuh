@@ -74,9 +74,7 @@ __host__ __device__ inline void uniform_pair(unsigned long long seed, unsigned l
 // operations per word), and ONE exact subtraction gives u; the affine map of the prior is then the usual fma(u, b - a, a),
 // which keeps every draw inside [a, b).  (The first version took two 53-bit uniforms per call: eight calls per sample and
 // five fp64 operations per uniform, a quarter of the reduce-only kernel's per-sample work.)
-__host__ __device__ inline void uniform_triple(unsigned long long seed, unsigned long long sample, uint32_t triple, double (&u)[3]) {
-    uint32_t o[4];
-    philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), triple, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+__host__ __device__ inline void triple_from_words(const uint32_t (&o)[4], double (&u)[3]) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const uint32_t top = j == 0 ? (o[3] << 10) : (j == 1 ? o[3] : (o[3] >> 10));   // 10 bits of word 3 at bits 10..19
@@ -90,6 +88,11 @@ __host__ __device__ inline void uniform_triple(unsigned long long seed, unsigned
         u[j] = d - 1.0;
 #endif
     }
+}
+__host__ __device__ inline void uniform_triple(unsigned long long seed, unsigned long long sample, uint32_t triple, double (&u)[3]) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), triple, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    triple_from_words(o, u);
 }
 
 // Normal(mean a, std b): Box-Muller with a second uniform from stream 1 of the same (sample, input).  Out of line: no prior
@@ -116,15 +119,30 @@ __device__ __forceinline__ double apply_prior(const Prior& pr, double u, unsigne
 // first, in ONE basic block, so their ten-round dependency chains interleave; then the affine maps; the exponentials of
 // the LogUniform inputs (and the rare Normal inputs) last, behind warp-uniform tests of the prior masks.  Values are
 // exactly those of apply_prior() applied input by input.
+// The generator half and the transform half are separate so that the reduce-only kernel can draw the NEXT batch's words
+// next to the latency-bound end of the current batch (integer work beside fp64 dependency chains).
+constexpr uint32_t kLogCandidates = (1u << 0) | (1u << 10) | (1u << 11);   // P_b, c4, c5: the LogUniform inputs of PEM v0
 template <int N>
-__device__ __forceinline__ void sample_inputs_n(const SamplerParams& sp, const unsigned long long (&local_index)[N], double (&x)[N][15]) {
-    double u[N][15];
+__device__ __forceinline__ void sample_words_n(const SamplerParams& sp, const unsigned long long (&local_index)[N], uint32_t (&o)[N][5][4]) {
 #pragma unroll
     for (uint32_t t = 0; t < 5; ++t) {
 #pragma unroll
         for (int s = 0; s < N; ++s) {
+            const unsigned long long sample = sp.first_index + local_index[s];
+            philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32), t, 0u, (uint32_t)sp.seed, (uint32_t)(sp.seed >> 32), o[s][t]);
+        }
+    }
+}
+template <int N>
+__device__ __forceinline__ void sample_transform_n(const SamplerParams& sp, const unsigned long long (&local_index)[N], const uint32_t (&o)[N][5][4],
+                                                   double (&x)[N][15]) {
+    double u[N][15];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+#pragma unroll
+        for (int s = 0; s < N; ++s) {
             double v[3];
-            uniform_triple(sp.seed, sp.first_index + local_index[s], t, v);
+            triple_from_words(o[s][t], v);
             u[s][3 * t] = v[0];
             u[s][3 * t + 1] = v[1];
             u[s][3 * t + 2] = v[2];
@@ -135,10 +153,23 @@ __device__ __forceinline__ void sample_inputs_n(const SamplerParams& sp, const u
 #pragma unroll
         for (int s = 0; s < N; ++s) x[s][k] = fma(u[s][k], sp.scale[k], sp.offset[k]);
     }
-    if (sp.log_mask) {
+    // LogUniform: the inputs that are LogUniform in PEM v0 get their exponentials unconditionally, in ONE basic block (3 N
+    // independent chains; fm_exp is branch-free and harmless on any input), selected by the mask; any other input with a
+    // LogUniform prior takes a warp-uniform branch of its own
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+        if (kLogCandidates & (1u << k)) {
+#pragma unroll
+            for (int s = 0; s < N; ++s) {
+                const double e = fm_exp(x[s][k]);
+                x[s][k] = (sp.log_mask & (1u << k)) ? e : x[s][k];
+            }
+        }
+    }
+    if (sp.log_mask & ~kLogCandidates) {
 #pragma unroll
         for (int k = 0; k < 15; ++k) {
-            if (sp.log_mask & (1u << k)) {
+            if (!(kLogCandidates & (1u << k)) && (sp.log_mask & (1u << k))) {
 #pragma unroll
                 for (int s = 0; s < N; ++s) x[s][k] = fm_exp(x[s][k]);   // branch-free, < 1 ulp (hpem_fastmath.cuh)
             }
@@ -154,6 +185,12 @@ __device__ __forceinline__ void sample_inputs_n(const SamplerParams& sp, const u
             }
         }
     }
+}
+template <int N>
+__device__ __forceinline__ void sample_inputs_n(const SamplerParams& sp, const unsigned long long (&local_index)[N], double (&x)[N][15]) {
+    uint32_t o[N][5][4];
+    sample_words_n<N>(sp, local_index, o);
+    sample_transform_n<N>(sp, local_index, o, x);
 }
 __device__ __forceinline__ void sample_inputs(const SamplerParams& sp, unsigned long long local_index, double x[15]) {
     const unsigned long long idx[1] = {local_index};
