@@ -33,6 +33,7 @@ FLAG_LANES1 = 4
 FLAG_LANES4 = 8
 FLAG_NO_QUAD = 16
 FLAG_NO_FASTMATH = 32
+FLAG_NO_QTABLE = 64
 
 EXPORTED_SYMBOLS = (
     'hpem_abi_version', 'hpem_source_hash', 'hpem_last_error', 'hpem_grid_create', 'hpem_grid_destroy', 'hpem_grid_is_uniform',

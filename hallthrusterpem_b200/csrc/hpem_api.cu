@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -79,8 +80,6 @@ struct Workspace {
     unsigned* d_hist_partials = nullptr;   // K2 per-block histograms; all-zero between calls (the finalize kernel re-zeroes them)
     size_t hist_partials_cap = 0;
     cudaEvent_t moments_done = nullptr;    // end of the last reduce-only pass that used the scratch buffers above
-    double* d_qtable = nullptr;            // K2: tabulated Simpson sums N_d(x), N_n(x) of this grid (hpem_qtable.cuh), built on first use
-    int qt_key_lo = 0, qt_bins = 0;
 };
 
 }  // namespace
@@ -95,6 +94,8 @@ struct hpem_grid {
     double* d_radii = nullptr;
     std::vector<double> alpha_host;
     std::vector<double2> w_host;   // fused weights (wd_i, wn_i), zero-padded
+    double* d_qtable = nullptr;    // uniform grids: tabulated Simpson sums N_d(x), N_n(x) (hpem_qtable.cuh)
+    int qt_key_lo = 0, qt_bins = 0;
     size_t smem_tma = 0, smem_tma32 = 0, smem_tma1 = 0, smem_quad = 0, smem_quad1 = 0, smem_stg = 0, smem_nostore = 0, smem_rows = 0;  // dynamic shared memory of the K1u variants
     size_t smem_v_store = 0, smem_v_nostore = 0;          // ... and of K1v
     int sm_count = 148;
@@ -156,6 +157,34 @@ void fill_params(const hpem_grid& g, const hpem_inputs& in, const hpem_outputs& 
     p.l2_hint = hint_env >= 0 ? hint_env : (((long long)g.n_angles * g.n_radii) % 16 == 0 ? 2 : 1);
     static const int no_fast_env = []() { const char* v = std::getenv("HPEM_NO_FASTMATH"); return v ? std::atoi(v) : 0; }();
     p.no_fastmath = no_fast_env;
+    static const int no_qtable_env = []() { const char* v = std::getenv("HPEM_NO_QTABLE"); return v ? std::atoi(v) : 0; }();
+    p.qt.rows = no_qtable_env ? nullptr : g.d_qtable;
+    p.qt.key_lo = g.qt_key_lo;
+    p.qt.n_bins = g.qt_bins;
+    p.qt.wd0 = g.w_host.empty() ? 0.0 : g.w_host[0].x;
+    p.qt.wn0 = g.w_host.empty() ? 0.0 : g.w_host[0].y;
+}
+
+// Host copies of the quadrature tables, one per distinct weight vector: several devices / radii sets share one build.
+struct QTableHost {
+    std::vector<double> wd, wn, rows;
+    int key_lo = 0, n_bins = 0;
+};
+std::shared_ptr<const QTableHost> qtable_for(int n_angles, const double* wd, const double* wn) {
+    static std::mutex mu;
+    static std::vector<std::shared_ptr<const QTableHost>> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto& t : cache)
+        if ((int)t->wd.size() == n_angles && std::memcmp(t->wd.data(), wd, n_angles * sizeof(double)) == 0 &&
+            std::memcmp(t->wn.data(), wn, n_angles * sizeof(double)) == 0)
+            return t;
+    auto t = std::make_shared<QTableHost>();
+    t->wd.assign(wd, wd + n_angles);
+    t->wn.assign(wn, wn + n_angles);
+    hpem::qtable_build(n_angles, wd, wn, t->rows, t->key_lo, t->n_bins);
+    if (cache.size() >= 32) cache.erase(cache.begin());
+    cache.push_back(t);
+    return t;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time dependency on libcuda)
@@ -372,6 +401,7 @@ int launch_range(const hpem_grid& g, const hpem_inputs& in, const hpem_outputs& 
     hpem::EvalParams p;
     fill_params(g, in, out, first, count, torr, p);
     if (flags & HPEM_FLAG_NO_FASTMATH) p.no_fastmath = 1;
+    if (flags & HPEM_FLAG_NO_QTABLE) p.qt.rows = nullptr;
     return launch(g, p, plume, store_j, flags, st);
 }
 
@@ -466,6 +496,13 @@ int hpem_grid_create(int device, int n_angles, const double* alpha, const double
     HPEM_CUDA_G(cudaMemcpy(g->d_w, w.data(), w.size() * sizeof(double2), cudaMemcpyHostToDevice));
     HPEM_CUDA_G(cudaMemcpy(g->d_alpha, alpha, n_angles * sizeof(double), cudaMemcpyHostToDevice));
     HPEM_CUDA_G(cudaMemcpy(g->d_radii, radii, n_radii * sizeof(double), cudaMemcpyHostToDevice));
+    if (g->uniform) {   // tabulated Simpson sums (host build: 20-170 ms for 91-512 angles, shared by the handles of one process)
+        std::shared_ptr<const QTableHost> t = qtable_for(n_angles, wd, wn);
+        g->qt_key_lo = t->key_lo;
+        g->qt_bins = t->n_bins;
+        HPEM_CUDA_G(cudaMalloc((void**)&g->d_qtable, t->rows.size() * sizeof(double)));
+        HPEM_CUDA_G(cudaMemcpy(g->d_qtable, t->rows.data(), t->rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
 #undef HPEM_CUDA_G
 
     const size_t wbytes = size_t(g->n_angles_pad) * sizeof(double2) + 1024;  // K1r / K1v: + slack for the 1024-byte alignment
@@ -518,7 +555,6 @@ int hpem_grid_destroy(hpem_grid* g) {
     if (ws.d_partials) cudaFree(ws.d_partials);
     if (ws.d_partial_minmax) cudaFree(ws.d_partial_minmax);
     if (ws.d_hist_partials) cudaFree(ws.d_hist_partials);
-    if (ws.d_qtable) cudaFree(ws.d_qtable);
     if (ws.moments_done) cudaEventDestroy(ws.moments_done);
     for (auto e : ws.events) cudaEventDestroy(e);
     for (auto e : ws.h2d_events) cudaEventDestroy(e);
@@ -528,6 +564,7 @@ int hpem_grid_destroy(hpem_grid* g) {
     if (g->d_w) cudaFree(g->d_w);
     if (g->d_alpha) cudaFree(g->d_alpha);
     if (g->d_radii) cudaFree(g->d_radii);
+    if (g->d_qtable) cudaFree(g->d_qtable);
     delete g;
     return HPEM_OK;
 }
@@ -878,18 +915,6 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
         HPEM_CUDA(cudaMemsetAsync(ws.d_hist_partials, 0, ws.hist_partials_cap * sizeof(unsigned), st));
     }
 
-    if (!ws.d_qtable) {     // the grid's quadrature table: built once (host, long double), kept with the handle
-        std::vector<double> wd(g->n_angles), wn(g->n_angles), rows;
-        for (int i = 0; i < g->n_angles; ++i) {
-            wd[i] = g->w_host[i].x;
-            wn[i] = g->w_host[i].y;
-        }
-        qtable_build(g->n_angles, wd.data(), wn.data(), rows, ws.qt_key_lo, ws.qt_bins);
-        HPEM_CUDA(cudaMalloc((void**)&ws.d_qtable, rows.size() * sizeof(double)));
-        HPEM_CUDA(cudaMemcpyAsync(ws.d_qtable, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-        HPEM_CUDA(cudaStreamSynchronize(st));   // `rows` is pageable and dies with this scope
-    }
-
     hpem_outputs no_out = {};
     hpem_inputs no_in = {};
     EvalParams p;
@@ -897,12 +922,6 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
     p.has_thrust = spec->want_thrust != 0;
     MomentsParams m;
     fill_moments_params(*spec, lay, m);
-    static const int no_qtable_env = []() { const char* v = std::getenv("HPEM_NO_QTABLE"); return v ? std::atoi(v) : 0; }();
-    m.qt.rows = no_qtable_env ? nullptr : ws.d_qtable;
-    m.qt.key_lo = ws.qt_key_lo;
-    m.qt.n_bins = ws.qt_bins;
-    m.qt.wd0 = g->w_host[0].x;
-    m.qt.wn0 = g->w_host[0].y;
     m.partials = ws.d_partials;
     m.partial_minmax = ws.d_partial_minmax;
     m.hist_partials = ws.d_hist_partials;

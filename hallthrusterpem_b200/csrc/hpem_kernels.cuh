@@ -27,6 +27,7 @@
 #include <type_traits>
 
 #include "hpem_device.cuh"
+#include "hpem_qtable.cuh"
 #include "hpem_sampler.cuh"
 
 namespace hpem {
@@ -65,6 +66,7 @@ struct EvalParams {
     int q_lead[4], q_tail[4], q_body;
     int l2_hint;             // K1u tensor stores: 0 normal, 1 evict_last, 2 evict_first (see l2_store_policy)
     int no_fastmath;         // 1: always take the libdevice back end for the per-sample part (HPEM_FLAG_NO_FASTMATH)
+    QTableRef qt;            // the grid's tabulated Simpson sums (hpem_qtable.cuh); rows == nullptr: sum angle by angle
 };
 
 struct JMaps {               // tensor maps of j_ion: [0] the (n, A) view; quad-row mode: one pair per row phase
@@ -342,6 +344,11 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
     BeamState b1, b2;
     double v_cc = 0.0, j_cex = 0.0, base = 0.0;
     double u1 = 0.0, u2 = 0.0;                   // exp(-x) of the two beams (quad mode: the lead elements need E(1), E(2))
+    double num = 0.0, den = 0.0;                 // the Simpson sums of plume.py:121-122
+    // Only the variant that stores no j_ion takes the sums from the grid's table (and then needs no sweep at all).  With
+    // stores the table loses: two divergent 160-byte lookups per sample are ~45 % more L2 read traffic next to the store
+    // stream (B200, 1e6 x 91: 0.163 -> 0.210 ms; x 200: 0.316 -> 0.333 ms), more than the two fused multiply-adds per angle cost.
+    const bool use_qt = !STORE_J && p.qt.rows != nullptr;
     auto prologue = [&](auto fast_tag) {
         constexpr bool FAST = decltype(fast_tag)::value;
         if (want_cathode)
@@ -356,6 +363,15 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
             } else {
                 beam_init<FAST>(b1, p.h, k.a1, __dmul_rn(base, k.amp1));   // (base_density * A1), plume.py:99
                 beam_init<FAST>(b2, p.h, k.a2, __dmul_rn(base, k.amp2));   // (base_density * A2), plume.py:100
+                u1 = b1.rc;
+                u2 = b2.rc;
+            }
+            if (FAST && use_qt) {   // both sums from the grid's table: amplitude x N((h / alpha)^2) per beam (hpem_qtable.cuh)
+                double nd1, nn1, nd2, nn2;
+                qtable_eval(p.qt, b1.x, u1, nd1, nn1);
+                qtable_eval(p.qt, b2.x, u2, nd2, nn2);
+                den = fma(b1.amp, nd1, b2.amp * nd2);
+                num = fma(b1.amp, nn1, b2.amp * nn2);
             }
         }
     };
@@ -373,7 +389,10 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
     // `j_ion <= 0` test of plume.py:105 cannot fire; only warps holding an exceptional sample run the checked loop.
     const bool needs_check = known_invalid || !(b1.amp >= 0.0 && b2.amp >= 0.0 && j_cex > 0.0);
     bool bad = false;
-    double num = 0.0, den = 0.0;
+    // no j_ion wanted: warps of the fast back end whose rows need no validity check hold the two sums already (table) and
+    // skip the sweep; every other warp accumulates them angle by angle
+    const bool tabulated = fast && use_qt && !__any_sync(0xffffffffu, needs_check);
+    if (!tabulated) num = den = 0.0;
 
     const int A = p.n_angles;
     const int A_sweep = QUAD ? p.q_body : A;     // angles covered by the chunked sweep
@@ -520,10 +539,13 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
             }
         }
     };
-    if (__any_sync(0xffffffffu, needs_check))
+    if (tabulated) {
+        // nothing to store and nothing to sum: div_angle / T_c / cos_div need no sweep at all
+    } else if (__any_sync(0xffffffffu, needs_check)) {
         chunk_loop(std::true_type{});
-    else
+    } else {
         chunk_loop(std::false_type{});
+    }
 
     if (QUAD) {
         if (STORE_J) {   // the row-boundary buffer aliases the staging area: every tensor store must have read its tile

@@ -24,7 +24,6 @@
 // comes from E[x^2] - E[x]^2.  The per-sample scalars are accumulated about a caller-supplied shift.
 #pragma once
 #include "hpem_kernels.cuh"
-#include "hpem_qtable.cuh"
 
 namespace hpem {
 
@@ -41,7 +40,6 @@ struct MomentsParams {
     double* partials;     // [gridDim.x][n_part]   n_part = kMomScalars + 2 A   (raw sums of one block)
     double* partial_minmax;  // [gridDim.x][6]  (-min, max) x (V_cc, div_angle, T_c)
     unsigned* hist_partials; // [gridDim.x][n_hist_angles][n_bins]   zero on entry, re-zeroed by the finalize kernel
-    QTableRef qt;         // tabulated Simpson sums of the grid (rows == nullptr: accumulate them angle by angle)
 };
 constexpr int kMomScalars = 12;  // n_samples n_invalid n_nonfinite_rows | {n_finite sum M2} x {V_cc div_angle T_c}
 #ifndef HPEM_THREADS_M
@@ -184,7 +182,7 @@ __global__ void __launch_bounds__(RESTART ? kWarpsLongM * 32 : kThreadsM, 1) mom
         double bx1[2], bx2[2], bamp1[2], bamp2[2];     // recurrence exponents / amplitudes (restarts, row checks)
         double v_cc[2] = {0.0, 0.0}, j_cex[2], a1v[2];
         double num[2] = {0.0, 0.0}, den[2] = {0.0, 0.0};   // the Simpson sums of plume.py:121-122
-        const bool use_qt = m.qt.rows != nullptr;
+        const bool use_qt = p.qt.rows != nullptr;
         auto prologue = [&](auto fast_tag) {
             constexpr bool FAST = decltype(fast_tag)::value;
 #pragma unroll
@@ -206,8 +204,8 @@ __global__ void __launch_bounds__(RESTART ? kWarpsLongM * 32 : kThreadsM, 1) mom
                 sweep_beam_init<FAST>(b2[u], bx2[u], p.h, k.a2);
                 if (FAST && use_qt) {   // both sums from the grid's table: amplitude x N(x) per beam (hpem_qtable.cuh)
                     double nd1, nn1, nd2, nn2;
-                    qtable_eval(m.qt, bx1[u], b1[u].rc, nd1, nn1);
-                    qtable_eval(m.qt, bx2[u], b2[u].rc, nd2, nn2);
+                    qtable_eval(p.qt, bx1[u], b1[u].rc, nd1, nn1);
+                    qtable_eval(p.qt, bx2[u], b2[u].rc, nd2, nn2);
                     den[u] = fma(bamp1[u], nd1, bamp2[u] * nd2);
                     num[u] = fma(bamp1[u], nn1, bamp2[u] * nn2);
                 }

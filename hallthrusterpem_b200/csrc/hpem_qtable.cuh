@@ -69,23 +69,61 @@ inline void qtable_build(int n_angles, const double* wd, const double* wn, std::
         for (int j = 0; j < nn; ++j) mono[k][j] = (j > 0 ? 2.0L * mono[k - 1][j - 1] : 0.0L) - mono[k - 2][j];
     std::vector<ld> kk(n_angles);            // i^2 - 1
     for (int i = 1; i < n_angles; ++i) kk[i] = ld(i) * ld(i) - 1.0L;
+    // terms with x (i^2 - 1) > 50 are below 2e-22 of the i = 1 term: the sums stop at i_max(x)
     auto m_sums = [&](ld x, ld& md, ld& mn) {
         md = mn = 0.0L;
-        for (int i = n_angles - 1; i >= 1; --i) {      // small terms first
-            const ld a = x * kk[i];
-            if (a > 11400.0L) continue;                // expl underflows
-            const ld e = expl(-a);
+        int i_max = n_angles - 1;
+        const ld lim = 50.0L / x + 1.0L;
+        if (lim < ld(i_max) * ld(i_max)) i_max = int(sqrtl(lim)) + 1;
+        if (i_max > n_angles - 1) i_max = n_angles - 1;
+        for (int i = i_max; i >= 1; --i) {             // small terms first
+            const ld e = expl(-x * kk[i]);
             md += ld(wd[i]) * e;
             mn += ld(wn[i]) * e;
         }
     };
+    // small x: M(x) = sum_k mu_k x^k, mu_k = (-1)^k / k! sum_i w_i (i^2 - 1)^k; with x A^2 < 2^-8 twelve terms reach 2^-96
+    constexpr int kTaylor = 12;
+    ld mu_d[kTaylor], mu_n[kTaylor];
+    {
+        std::vector<ld> pw(n_angles, 1.0L);
+        ld fact = 1.0L;
+        for (int k = 0; k < kTaylor; ++k) {
+            if (k > 0) fact *= -ld(k);               // (-1)^k k!
+            ld sd = 0.0L, sn = 0.0L;
+            for (int i = n_angles - 1; i >= 1; --i) {
+                sd += ld(wd[i]) * pw[i];
+                sn += ld(wn[i]) * pw[i];
+                pw[i] *= kk[i];
+            }
+            mu_d[k] = sd / fact;
+            mu_n[k] = sn / fact;
+        }
+    }
+    const ld a2 = ld(n_angles) * ld(n_angles);
     for (int b = 0; b < n_regular; ++b) {
         const int e2 = lo + b / nsub, m = b % nsub;
         const ld width = ldexpl(1.0L, e2) / nsub, xa = ldexpl(1.0L, e2) + m * width, xc = xa + 0.5L * width, delta = 0.5L * width / xc;
-        ld fd[kQtDeg + 1], fn[kQtDeg + 1];
-        for (int j = 0; j < nn; ++j) m_sums(xc * (1.0L + delta * s[j]), fd[j], fn[j]);
         double* row = rows.data() + size_t(b + 1) * kQtRow;
         row[0] = double(1.0L / xc);
+        if ((xa + width) * a2 < 0.00390625L) {
+            // M(xc (1 + t)) = sum_k mu_k xc^k (1 + t)^k  ->  coefficient of t^j = sum_{k >= j} mu_k xc^k C(k, j)
+            for (int f = 0; f < 2; ++f) {
+                const ld* mu = f ? mu_n : mu_d;
+                for (int j = 0; j < nn; ++j) {
+                    ld c = 0.0L, xk = powl(xc, j), binom = 1.0L;      // C(j, j)
+                    for (int k = j; k < kTaylor; ++k) {
+                        c += mu[k] * xk * binom;
+                        xk *= xc;
+                        binom = binom * ld(k + 1) / ld(k + 1 - j);   // C(k+1, j)
+                    }
+                    row[1 + f * nn + j] = double(c);
+                }
+            }
+            continue;
+        }
+        ld fd[kQtDeg + 1], fn[kQtDeg + 1];
+        for (int j = 0; j < nn; ++j) m_sums(xc * (1.0L + delta * s[j]), fd[j], fn[j]);
         for (int f = 0; f < 2; ++f) {
             const ld* fv = f ? fn : fd;
             ld cheb[kQtDeg + 1], poly[kQtDeg + 1];

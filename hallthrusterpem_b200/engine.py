@@ -337,7 +337,8 @@ class PreparedCall:
     def __init__(self, inputs: dict, *, want_cathode: bool, want_plume: bool, sweep_radius=1.0, n_angles: int = 91,
                  torr: float | None = None, device=None, direct: bool = False,
                  want_j_ion: bool = True, extras: bool = False, pin_outputs: bool = True, no_tma: bool = False,
-                 lanes1: bool = False, lanes4: bool = False, no_quad: bool = False, no_fastmath: bool = False):
+                 lanes1: bool = False, lanes4: bool = False, no_quad: bool = False, no_fastmath: bool = False,
+                 no_qtable: bool = False):
         self.lib = _lib.load()
         names: tuple[str, ...] = ()
         if want_cathode:
@@ -403,7 +404,7 @@ class PreparedCall:
                 result['invalid'], out.invalid = new(loop, np.uint8)
         self.flags = (_lib.FLAG_FORCE_DIRECT if direct else 0) | (_lib.FLAG_NO_TMA if no_tma else 0) \
             | (_lib.FLAG_LANES1 if lanes1 else 0) | (_lib.FLAG_LANES4 if lanes4 else 0) | (_lib.FLAG_NO_QUAD if no_quad else 0) \
-            | (_lib.FLAG_NO_FASTMATH if no_fastmath else 0)
+            | (_lib.FLAG_NO_FASTMATH if no_fastmath else 0) | (_lib.FLAG_NO_QTABLE if no_qtable else 0)
         self.h2d_bytes = 0 if batch.on_device else 8 * batch.n * sum(1 for k in range(_lib.N_INPUTS)
                                                                       if batch.struct.ptr[k])
         self.d2h_bytes = 0 if batch.on_device else sum(v.nbytes for v in result.values())

@@ -101,6 +101,9 @@ typedef struct hpem_outputs {
                                      in the nominal range (default: the branch-free functions of csrc/hpem_fastmath.cuh;   \
                                      both back ends meet the rel-1e-12 parity rule, they differ in last bits) */
 
+#define HPEM_FLAG_NO_QTABLE 64u    /* uniform grids: accumulate the two Simpson sums of plume.py:121-122 angle by angle instead of  \
+                                     taking them from the grid's table (csrc/hpem_qtable.cuh; the two agree to ~4e-16) */
+
 typedef struct hpem_grid hpem_grid; /* opaque */
 
 int hpem_abi_version(void);

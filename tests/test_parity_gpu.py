@@ -104,6 +104,40 @@ def test_separate_functions_match_fused(cuda_device):
     assert set(p) == {'j_ion', 'div_angle', 'T_c', 'j_ion_coords'} and set(v) == {'V_cc'}
 
 
+@pytest.mark.parametrize('n_angles', [91, 100, 200, 512])
+def test_per_sample_outputs_without_j_ion_use_the_quadrature_table(n_angles, cuda_device):
+    """want_j_ion=False: the two Simpson sums come from the grid's table (csrc/hpem_qtable.cuh) and no sweep runs.  The
+    per-sample outputs must meet the oracle's parity rule and agree with the summed path (and with the full evaluation)
+    far inside it, for ordinary samples and for the hand-built edge rows (invalid, NaN, needle beams, clipped alpha1)."""
+    from hallthrusterpem_b200.synthetic import spt100_batch
+    from oracle.make_golden import edge_batch
+    from oracle.ref_restated import cathode_coupling_oracle, current_density_oracle
+    from tests.parity import check_div_angle, check_rel
+    _, _, plume_cathode = _models()
+    torr = 133.322
+    e, r = edge_batch(), spt100_batch(3000, 4000 + n_angles)
+    b = {k: np.concatenate([e[k], r[k]]) for k in e}
+    with np.errstate(all='ignore'):
+        ref = current_density_oracle(b, 1.0, n_angles, torr, with_coords=False, return_internals=True)
+        v_ref = cathode_coupling_oracle(b, torr)['V_cc']
+    tab = plume_cathode(b, 1.0, n_angles=n_angles, torr_2_pa=torr, extras=True, want_j_ion=False)
+    summed = plume_cathode(b, 1.0, n_angles=n_angles, torr_2_pa=torr, extras=True, want_j_ion=False, no_qtable=True)
+    full = plume_cathode(b, 1.0, n_angles=n_angles, torr_2_pa=torr, extras=True)
+    assert 'j_ion' not in tab
+    for out, name in ((tab, 'table'), (summed, 'summed')):
+        check_rel(out['cos_div'], ref['_cos_div'], f'cos_div[{name}]')
+        check_rel(out['T_c'], ref['T_c'], f'T_c[{name}]')
+        check_div_angle(out['div_angle'], ref['div_angle'], out['cos_div'], ref['_cos_div'], f'div_angle[{name}]')
+        assert np.array_equal(out['invalid'].astype(bool), ref['_invalid'])
+        assert np.array_equal(out['V_cc'], full['V_cc'], equal_nan=True)
+    check_rel(tab['V_cc'], v_ref, 'V_cc', rtol=1e-9)     # (exact rule: the golden tests; here only that it is there)
+    # table vs angle-by-angle sums: both are ~1e-15 from the exact Simpson sums
+    ok = np.isfinite(full['cos_div'])
+    assert np.array_equal(np.isnan(tab['cos_div']), np.isnan(full['cos_div']))
+    assert np.max(np.abs(tab['cos_div'][ok] / full['cos_div'][ok] - 1)) < 2e-13
+    assert np.max(np.abs(tab['cos_div'][ok] / summed['cos_div'][ok] - 1)) < 2e-13
+
+
 @pytest.mark.parametrize('n,n_angles', [(1, 91), (31, 91), (33, 100), (1000, 100), (4097, 200), (20000, 256), (3000, 512),
                                         (777, 17), (500, 16), (500, 15), (100, 2), (100, 3)])
 def test_against_oracle_seeded(n, n_angles, cuda_device):
