@@ -143,11 +143,12 @@ def main():
             'samples/s', '200000 samples x 15 inputs, numpy Generator.uniform (+exp for the 3 LogUniform inputs)')
     emit('f3', 'sample_inputs_kernel', f'{n} samples x 15 inputs (SPT-100 priors)', n, 'samples/s', ms, 'hbm', 120.0, '120 B/sample (15 fp64 stores)', c)
     for A, stride in ((256, 8), (512, 8), (91, 8)):
-        n = 8_000_000 if A < 512 else 4_000_000
+        n = 40_000_000
         mc = MonteCarloMoments(n_angles=A, device=0, hist=HistogramSpec(angle_stride=stride))
         ms = gpu_ms(lambda: mc.accumulate_sampled(n, 7, 0), reps=5, warm=2)
         emit('f3+e/K2', 'moments_kernel<sampled>', f'reduce-only MC, {n} samples x {A} angles, inputs drawn on device, histogram every '
-             f'{stride}th angle', n * A, 'evals/s', ms, 'fp64', 10.0, '10 fp64 instr/eval (8 recurrence sweep + 2 per-angle sum / sum of squares)')
+             f'{stride}th angle', n * A, 'evals/s', ms, 'fp64', 10.0, '10 fp64 instr/eval: the reduce-only algorithm (8 recurrence sweep incl. the two Simpson sums + sum + sum of squares); '
+             'the kernel executes 8.8 in its sweep since the Simpson sums come from the per-grid table')
 
     # ---- (f4) SVD compression ----
     for A in (91, 200):

@@ -27,9 +27,9 @@ if what in ('k1u', 'k1q'):
         call.run()
 elif what in ('k2', 'k2s'):
     from hallthrusterpem_b200.mc import HistogramSpec, MonteCarloMoments
-    n = 2_000_000
+    n = 8_000_000 if what == 'k2s' else 2_000_000
     mc = MonteCarloMoments(n_angles=int(os.environ.get('K2_A', 256)), device=0, hist=HistogramSpec(angle_stride=8))
-    b = dev(spt100_batch(n, 1))
+    b = dev(spt100_batch(min(n, 2_000_000), 1))
     for _ in range(3):
         mc.accumulate_sampled(n, 7, 0) if what == 'k2s' else mc.accumulate(b)
 elif what == 'k3':
