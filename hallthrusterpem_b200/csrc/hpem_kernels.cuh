@@ -348,7 +348,8 @@ eval_uniform_kernel(const EvalParams p, const __grid_constant__ JMaps maps) {
     // Only the variant that stores no j_ion takes the sums from the grid's table (and then needs no sweep at all).  With
     // stores the table loses: two divergent 160-byte lookups per sample are ~45 % more L2 read traffic next to the store
     // stream (B200, 1e6 x 91: 0.163 -> 0.210 ms; x 200: 0.316 -> 0.333 ms), more than the two fused multiply-adds per angle cost.
-    const bool use_qt = !STORE_J && p.qt.rows != nullptr;
+    // (below ~50 angles the two lookups cost more than the sweep they replace: 1e6 x 17 no-store 0.083 vs 0.092 ms)
+    const bool use_qt = !STORE_J && p.qt.rows != nullptr && p.n_angles >= 64;
     auto prologue = [&](auto fast_tag) {
         constexpr bool FAST = decltype(fast_tag)::value;
         if (want_cathode)

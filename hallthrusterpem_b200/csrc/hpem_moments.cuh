@@ -5,16 +5,18 @@
 // configs 4-5: 1e8-1e9 samples x up to 512 angles).
 //
 // Mapping.  One persistent block per SM; every THREAD owns TWO samples (s, s + 32) and runs their recurrence sweeps
-// (same arithmetic as K1u) interleaved: four independent multiply chains per thread, and the per-sample prologue of both
-// samples is one branch-free block (hpem_fastmath.cuh) that the compiler schedules as ~14 independent exp/log/division
-// chains.  The per-angle sums over samples need a transposition (thread = sample for the sweep and the quadrature,
-// thread = angle for the column sums).  The two samples of a thread are combined in registers first,
+// (same arithmetic as K1u) interleaved: eight independent multiply chains per thread, and the per-sample prologue of both
+// samples is one branch-free block (hpem_fastmath.cuh).  The Philox words of a batch are drawn one iteration ahead, beside
+// the latency-bound tail of the previous batch.  The two Simpson sums of plume.py:121-122 come from the grid's table
+// (hpem_qtable.cuh): one lookup per beam instead of two fused multiply-adds per (sample, angle).  The per-angle sums over
+// samples need a transposition (thread = sample for the sweep, thread = angle for the column sums).  The two samples of a
+// thread are combined in registers first,
 //        t = jA + jB,   q = jA^2 + jB^2,
 // so the tile that goes through shared memory holds one (t, q) pair per TWO evaluations: 16-byte conflict-free
-// stores, 16-byte column loads, half the shared-memory traffic of a value-per-evaluation tile (the first version was as
-// busy on the shared-memory pipe as on the fp64 pipe).  Column sums: 2 lanes per angle, 16 rows each, added into
-// per-warp accumulators; one partial vector per block at the end, merged in block order by moments_finalize_kernel
-// (bit-reproducible for a fixed launch geometry).
+// stores, half the shared-memory traffic of a value-per-evaluation tile (the first version was as busy on the
+// shared-memory pipe as on the fp64 pipe).  Column sums: 2 lanes per column of 16 rows, added into per-warp accumulators;
+// one partial vector per block at the end, merged in block order by moments_finalize_kernel (bit-reproducible for a
+// fixed launch geometry).
 //
 // Histograms: log-linear bins straight from the leading bits of the fp64 pattern (no log), one fire-and-forget reduction
 // per lane to the block's private histogram in global memory (L2 atomics; blocks never share a line) -- see hist_add.

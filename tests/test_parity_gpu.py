@@ -104,9 +104,9 @@ def test_separate_functions_match_fused(cuda_device):
     assert set(p) == {'j_ion', 'div_angle', 'T_c', 'j_ion_coords'} and set(v) == {'V_cc'}
 
 
-@pytest.mark.parametrize('n_angles', [91, 100, 200, 512])
+@pytest.mark.parametrize('n_angles', [33, 91, 100, 200, 512])
 def test_per_sample_outputs_without_j_ion_use_the_quadrature_table(n_angles, cuda_device):
-    """want_j_ion=False: the two Simpson sums come from the grid's table (csrc/hpem_qtable.cuh) and no sweep runs.  The
+    """want_j_ion=False, 64 angles and more: the two Simpson sums come from the grid's table (csrc/hpem_qtable.cuh) and no sweep runs.  The
     per-sample outputs must meet the oracle's parity rule and agree with the summed path (and with the full evaluation)
     far inside it, for ordinary samples and for the hand-built edge rows (invalid, NaN, needle beams, clipped alpha1)."""
     from hallthrusterpem_b200.synthetic import spt100_batch
