@@ -496,7 +496,7 @@ int hpem_grid_create(int device, int n_angles, const double* alpha, const double
     HPEM_CUDA_G(cudaMemcpy(g->d_w, w.data(), w.size() * sizeof(double2), cudaMemcpyHostToDevice));
     HPEM_CUDA_G(cudaMemcpy(g->d_alpha, alpha, n_angles * sizeof(double), cudaMemcpyHostToDevice));
     HPEM_CUDA_G(cudaMemcpy(g->d_radii, radii, n_radii * sizeof(double), cudaMemcpyHostToDevice));
-    if (g->uniform) {   // tabulated Simpson sums (host build: 20-170 ms for 91-512 angles, shared by the handles of one process)
+    if (g->uniform && n_angles <= 2048) {   // tabulated Simpson sums (host build: 20-170 ms for 91-512 angles, 0.5 s for 2048; shared by the handles of one process)
         std::shared_ptr<const QTableHost> t = qtable_for(n_angles, wd, wn);
         g->qt_key_lo = t->key_lo;
         g->qt_bins = t->n_bins;
