@@ -886,15 +886,18 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
     const size_t smem_budget = (size_t)dev_smem - 4096;   // static shared memory of the kernel + slack
     static const int warps_env = []() { const char* v = std::getenv("HPEM_MOMENTS_WARPS"); return v ? std::atoi(v) : 0; }();
     const bool restart = n_chunks > kRestartChunks;
-    const int max_warps = restart ? kWarpsLongM : kMaxWarpsM;      // the launch bounds of the two kernel families
+    const int hs = spec->hist_angle_stride == 0 ? 0 : (spec->hist_angle_stride == 8 ? 8 : -1);
+    static const int ns_env = []() { const char* v = std::getenv("HPEM_MOMENTS_NS"); return v ? std::atoi(v) : 0; }();
+    // three samples per thread for long rows (instantiated for the two common histogram settings), two otherwise
+    const int ns = (hs != -1 && (restart || (ns_env ? ns_env == 3 : n_chunks >= kLongChunksM))) ? 3 : 2;   // restart rows of strides 0 / 8 exist with three samples only
+    const int max_warps = (restart || ns == 3) ? kWarpsLongM : kMaxWarpsM;      // the launch bounds of the kernel families
     int warps = warps_env > 0 ? std::min(warps_env, max_warps) : max_warps;
     while (warps > 1 && moments_smem_bytes(g->n_angles_pad, n_chunks * kChunk, warps) > smem_budget) --warps;
     const size_t smem = moments_smem_bytes(g->n_angles_pad, n_chunks * kChunk, warps);
     if (smem > smem_budget)
         return fail(HPEM_ERR_UNSUPPORTED, "%d angles need %zu bytes of shared memory (> %zu)", g->n_angles, smem, smem_budget);
-    const int hs = spec->hist_angle_stride == 0 ? 0 : (spec->hist_angle_stride == 8 ? 8 : -1);
     const int threads = warps * 32;
-    const int64_t batches = (n + 2 * threads - 1) / (2 * threads);
+    const int64_t batches = (n + (int64_t)ns * threads - 1) / ((int64_t)ns * threads);
     const int blocks = (int)std::min<int64_t>(batches, (int64_t)g->sm_count);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Workspace& ws = g->ws;
@@ -928,17 +931,26 @@ static int moments_run(hpem_grid* g, int64_t n, const hpem_inputs* in, const hpe
     SamplerParams sp_zero;
     std::memset(&sp_zero, 0, sizeof(sp_zero));
     const SamplerParams& sp = sampler ? *sampler : sp_zero;
-#define HPEM_MOMENTS_GO(S, H, R)                                        \
-    do {                                                                \
-        rc = set_smem(moments_kernel<S, H, R>, smem);                   \
-        if (rc != HPEM_OK) return rc;                                   \
-        moments_kernel<S, H, R><<<blocks, threads, smem, st>>>(p, m, sp); \
+#define HPEM_MOMENTS_GO(S, H, R, N)                                        \
+    do {                                                                   \
+        rc = set_smem(moments_kernel<S, H, R, N>, smem);                   \
+        if (rc != HPEM_OK) return rc;                                      \
+        moments_kernel<S, H, R, N><<<blocks, threads, smem, st>>>(p, m, sp); \
     } while (0)
-#define HPEM_MOMENTS_GO_R(S, H) do { if (restart) HPEM_MOMENTS_GO(S, H, true); else HPEM_MOMENTS_GO(S, H, false); } while (0)
-#define HPEM_MOMENTS_GO_H(S) do { if (hs == 0) HPEM_MOMENTS_GO_R(S, 0); else if (hs == 8) HPEM_MOMENTS_GO_R(S, 8); else HPEM_MOMENTS_GO_R(S, -1); } while (0)
+// instantiated: two samples per thread for every (stride, restart) except the long rows of the two common strides, which
+// exist with three samples only; three samples for strides 0 and 8
+#define HPEM_MOMENTS_GO_N(S, H, R)                                         \
+    do {                                                                   \
+        if (ns == 3) HPEM_MOMENTS_GO(S, H, R, 3); else HPEM_MOMENTS_GO(S, H, false, 2); \
+    } while (0)
+#define HPEM_MOMENTS_GO_R(S, H) do { if (restart) HPEM_MOMENTS_GO_N(S, H, true); else HPEM_MOMENTS_GO_N(S, H, false); } while (0)
+#define HPEM_MOMENTS_GO_ANY(S) do { if (restart) HPEM_MOMENTS_GO(S, -1, true, 2); else HPEM_MOMENTS_GO(S, -1, false, 2); } while (0)
+#define HPEM_MOMENTS_GO_H(S) do { if (hs == 0) HPEM_MOMENTS_GO_R(S, 0); else if (hs == 8) HPEM_MOMENTS_GO_R(S, 8); else HPEM_MOMENTS_GO_ANY(S); } while (0)
     if (sampler) HPEM_MOMENTS_GO_H(true); else HPEM_MOMENTS_GO_H(false);
 #undef HPEM_MOMENTS_GO_H
+#undef HPEM_MOMENTS_GO_ANY
 #undef HPEM_MOMENTS_GO_R
+#undef HPEM_MOMENTS_GO_N
 #undef HPEM_MOMENTS_GO
     HPEM_CUDA(cudaGetLastError());
     const int fthreads = 128;

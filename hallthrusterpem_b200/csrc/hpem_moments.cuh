@@ -107,11 +107,18 @@ __device__ __forceinline__ void hist_add(unsigned* hrow, double j, bool ok, int 
 // footprint leaves the L1 to the quadrature table (B200, 4e7 samples, histograms: 272 angles 9.5 -> 9.8e11 evals/s,
 // 512: 1.12 -> 1.20e12, 640: 1.10 -> 1.23e12; at 256 angles and below 12 warps stay 3-10 % ahead).  Registers come in
 // blocks of four warps, so 9-11 warps cannot have more than 168 either.
+//
+// NS = samples per thread.  Three samples on 8 warps x 255 registers keep as many samples in flight as two on 12 warps, with
+// a third fewer shared-memory stores, column-reduce additions and loop instructions per evaluation: ahead from ~200 angles
+// (4e7 samples, histograms: 224 angles +2 %, 256 +3 %, 512 +6 % over two samples on 8 warps), behind below (128: -2.5 %, 91:
+// -4 %: the per-sample part dominates there and wants the twelve warps).  Four samples spill (972 vs 1036e9 at 256 angles).
 constexpr int kWarpsLongM = 8;
-template <bool SAMPLED, int HS, bool RESTART>
-__global__ void __launch_bounds__(RESTART ? kWarpsLongM * 32 : kThreadsM, 1) moments_kernel(const EvalParams p, const MomentsParams m,
+constexpr int kLongChunksM = 13;     // rows of >= 13 chunks (> 192 angles) take the three-sample geometry (when instantiated)
+template <bool SAMPLED, int HS, bool RESTART, int NS>
+__global__ void __launch_bounds__((RESTART || NS > 2) ? kWarpsLongM * 32 : kThreadsM, 1) moments_kernel(const EvalParams p, const MomentsParams m,
                                                                const __grid_constant__ SamplerParams sp) {
     extern __shared__ __align__(16) unsigned char smem_m[];
+    constexpr int kNS = NS;
     const int A = p.n_angles;
     const int n_chunks = (A + kChunk - 1) / kChunk;
     const int a_pad = n_chunks * kChunk;
@@ -139,39 +146,39 @@ __global__ void __launch_bounds__(RESTART ? kWarpsLongM * 32 : kThreadsM, 1) mom
     const int h_mask = max(m.hist_stride, 1) - 1;
     unsigned* hist_blk = m.hist_partials + (size_t)blockIdx.x * m.n_hist_angles * m.n_bins;
 
-    const long long batch = (long long)n_warps * 64;
+    const long long batch = (long long)n_warps * (32 * kNS);
     // SAMPLED: the Philox words of a batch are drawn one iteration ahead, next to the latency-bound tail of the previous
     // batch (last column reduce, division, arccos), where the integer pipe is idle
-    uint32_t words[2][5][4];
+    uint32_t words[kNS][5][4];
     auto draw_words = [&](long long w0_next) {
-        unsigned long long nidx[2];
+        unsigned long long nidx[kNS];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kNS; ++u) {
             const long long s_raw = w0_next + u * 32 + lane;
             nidx[u] = (unsigned long long)(s_raw < p.n ? s_raw : p.n - 1);
         }
-        sample_words_n<2>(sp, nidx, words);
+        sample_words_n<kNS>(sp, nidx, words);
     };
-    if (SAMPLED) draw_words((long long)blockIdx.x * batch + warp * 64);
+    if (SAMPLED) draw_words((long long)blockIdx.x * batch + warp * (32 * kNS));
     for (long long b0 = (long long)blockIdx.x * batch; b0 < p.n; b0 += (long long)gridDim.x * batch) {
-        const long long w0 = b0 + warp * 64;
+        const long long w0 = b0 + warp * (32 * kNS);
         if (w0 >= p.n) continue;   // warp-uniform; no block-level barrier inside the loop (later batches of this warp are out of range too)
 
         // ---- the two samples of this thread: inputs ----
-        double x_in[2][kNumInputs];
-        bool active[2];
-        unsigned long long sidx[2];
+        double x_in[kNS][kNumInputs];
+        bool active[kNS];
+        unsigned long long sidx[kNS];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kNS; ++u) {
             const long long s_raw = w0 + u * 32 + lane;
             active[u] = s_raw < p.n;
             sidx[u] = (unsigned long long)(active[u] ? s_raw : p.n - 1);   // inactive lanes shadow the last sample, contribute nothing
         }
         if (SAMPLED) {
-            sample_transform_n<2>(sp, sidx, words, x_in);
+            sample_transform_n<kNS>(sp, sidx, words, x_in);
         } else {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < kNS; ++u) {
 #pragma unroll
                 for (int q = 0; q < kNumInputs; ++q) {
                     const bool needed = (q == IN_P_b) || (q <= IN_P_T ? want_cathode : (q == IN_T ? want_thrust : true));
@@ -180,21 +187,23 @@ __global__ void __launch_bounds__(RESTART ? kWarpsLongM * 32 : kThreadsM, 1) mom
             }
         }
         // ---- per-sample prologue, both samples in one basic block ----
-        SweepBeam b1[2], b2[2];
-        double bx1[2], bx2[2], bamp1[2], bamp2[2];     // recurrence exponents / amplitudes (restarts, row checks)
-        double v_cc[2] = {0.0, 0.0}, j_cex[2], a1v[2];
-        double num[2] = {0.0, 0.0}, den[2] = {0.0, 0.0};   // the Simpson sums of plume.py:121-122
+        SweepBeam b1[kNS], b2[kNS];
+        double bx1[kNS], bx2[kNS], bamp1[kNS], bamp2[kNS];     // recurrence exponents / amplitudes (restarts, row checks)
+        double v_cc[kNS], j_cex[kNS], a1v[kNS];
+        double num[kNS], den[kNS];
+#pragma unroll
+        for (int u = 0; u < kNS; ++u) v_cc[u] = num[u] = den[u] = 0.0;   // the Simpson sums of plume.py:121-122
         const bool use_qt = p.qt.rows != nullptr;
         auto prologue = [&](auto fast_tag) {
             constexpr bool FAST = decltype(fast_tag)::value;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < kNS; ++u) {
                 if (want_cathode)
                     v_cc[u] = cathode_vcc<FAST>(x_in[u][IN_P_b], x_in[u][IN_V_a], x_in[u][IN_T_e], x_in[u][IN_V_vac],
                                                 x_in[u][IN_Pstar], x_in[u][IN_P_T], p.torr);
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < kNS; ++u) {
                 const SampleConsts k = plume_sample_consts<FAST>(x_in[u][IN_P_b], x_in[u][IN_c0], x_in[u][IN_c1], x_in[u][IN_c2],
                                                                  x_in[u][IN_c3], x_in[u][IN_c4], x_in[u][IN_c5], p.torr);
                 double base;
@@ -213,18 +222,19 @@ __global__ void __launch_bounds__(RESTART ? kWarpsLongM * 32 : kThreadsM, 1) mom
                 }
             }
         };
-        const bool nominal = prologue_nominal(x_in[0], p.torr, want_cathode, true, p.radius0) &&
-                             prologue_nominal(x_in[1], p.torr, want_cathode, true, p.radius0);
+        bool nominal = true;
+#pragma unroll
+        for (int u = 0; u < kNS; ++u) nominal = nominal && prologue_nominal(x_in[u], p.torr, want_cathode, true, p.radius0);
         const bool fast = __all_sync(0xffffffffu, nominal) && !p.no_fastmath;
         if (fast)
             prologue(std::true_type{});
         else
             prologue(std::false_type{});
 
-        bool invalid[2], row_ok[2];
-        double thrust[2], j_fill[2];
+        bool invalid[kNS], row_ok[kNS];
+        double thrust[kNS], j_fill[kNS];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kNS; ++u) {
             thrust[u] = x_in[u][IN_T];
             if (want_cathode && active[u] && v_cc[u] == v_cc[u]) {
                 const double d = v_cc[u] - m.shift[0];
@@ -272,7 +282,10 @@ __global__ void __launch_bounds__(RESTART ? kWarpsLongM * 32 : kThreadsM, 1) mom
             j_fill[u] = row_ok[u] ? kInvalidFill : 0.0;
         }
         // warps whose 64 rows are all ordinary (finite, valid) -- virtually all of them -- skip the per-element selects
-        const bool plain = !__any_sync(0xffffffffu, invalid[0] || invalid[1] || !row_ok[0] || !row_ok[1]);
+        bool odd_row = false;
+#pragma unroll
+        for (int u = 0; u < kNS; ++u) odd_row = odd_row || invalid[u] || !row_ok[u];
+        const bool plain = !__any_sync(0xffffffffu, odd_row);
         // The 16-angle chunk goes through shared memory as two half-tiles of 8 angles, [32 rows][kHalfPitch] (t, q) pairs each.
         // While a thread sweeps one half it column-reduces the OTHER one, two rows per recurrence step, so the loads and
         // additions of the reduction are scheduled inside the fp64 stream of the sweep instead of forming a latency-bound
@@ -291,7 +304,10 @@ __global__ void __launch_bounds__(RESTART ? kWarpsLongM * 32 : kThreadsM, 1) mom
         // PLAIN warps (all rows ordinary) of the fast back end already hold the two Simpson sums (table); every other warp
         // accumulates them angle by angle and selects the fill value per element
         const bool tabulated = plain && fast && use_qt;
-        if (!tabulated) den[0] = den[1] = num[0] = num[1] = 0.0;
+        if (!tabulated) {
+#pragma unroll
+            for (int u = 0; u < kNS; ++u) den[u] = num[u] = 0.0;
+        }
         auto sweep = [&](auto plain_tag) {
             constexpr bool PLAIN = decltype(plain_tag)::value;
             unsigned* hrow = hist_blk;                       // histogram row of the next histogrammed angle
@@ -307,13 +323,13 @@ __global__ void __launch_bounds__(RESTART ? kWarpsLongM * 32 : kThreadsM, 1) mom
                 if (RESTART && c != 0 && (c % kRestartChunks) == 0) {
                     if (fast) {      // all 64 samples nominal: twelve branch-free exps as one block (neutralised rows have x = 0: exp(0) = 1)
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
+                        for (int u = 0; u < kNS; ++u) {
                             sweep_beam_restart<true>(b1[u], bx1[u], i0);
                             sweep_beam_restart<true>(b2[u], bx2[u], i0);
                         }
                     } else {
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
+                        for (int u = 0; u < kNS; ++u) {
                             if (row_ok[u]) {
                                 sweep_beam_restart(b1[u], bx1[u], i0);
                                 sweep_beam_restart(b2[u], bx2[u], i0);
@@ -321,38 +337,50 @@ __global__ void __launch_bounds__(RESTART ? kWarpsLongM * 32 : kThreadsM, 1) mom
                         }
                     }
                 }
-                double e1a = bamp1[0] * b1[0].ec, e2a = bamp2[0] * b2[0].ec, r1a = b1[0].rc, r2a = b2[0].rc;
-                double e1b = bamp1[1] * b1[1].ec, e2b = bamp2[1] * b2[1].ec, r1b = b1[1].rc, r2b = b2[1].rc;
+                double e1[kNS], e2[kNS], r1[kNS], r2[kNS];
+#pragma unroll
+                for (int u = 0; u < kNS; ++u) {
+                    e1[u] = bamp1[u] * b1[u].ec;
+                    e2[u] = bamp2[u] * b2[u].ec;
+                    r1[u] = b1[u].rc;
+                    r2[u] = b2[u].rc;
+                }
 #pragma unroll
                 for (int kk = 0; kk < kChunk; ++kk) {
-                    const double sa = e1a + e2a, sb = e1b + e2b;   // j_beam + j_scat
-                    if (!PLAIN) {
-                        const double2 w = wsm[i0 + kk];      // zero beyond A
-                        den[0] = fma(w.x, sa, den[0]);
-                        num[0] = fma(w.y, sa, num[0]);
-                        den[1] = fma(w.x, sb, den[1]);
-                        num[1] = fma(w.y, sb, num[1]);
+                    double jv[kNS];
+#pragma unroll
+                    for (int u = 0; u < kNS; ++u) {
+                        const double su = e1[u] + e2[u];     // j_beam + j_scat
+                        if (!PLAIN) {
+                            const double2 w = wsm[i0 + kk];  // zero beyond A
+                            den[u] = fma(w.x, su, den[u]);
+                            num[u] = fma(w.y, su, num[u]);
+                        }
+                        jv[u] = su + j_cex[u];               // the values current_density() returns (plume.py:102)
+                        if (!PLAIN) jv[u] = invalid[u] ? j_fill[u] : jv[u];
                     }
-                    double ja = sa + j_cex[0], jb = sb + j_cex[1];  // the values current_density() returns (plume.py:102)
-                    if (!PLAIN) {
-                        ja = invalid[0] ? j_fill[0] : ja;
-                        jb = invalid[1] ? j_fill[1] : jb;
+                    double tsum = jv[0], qsum = jv[0] * jv[0];
+#pragma unroll
+                    for (int u = 1; u < kNS; ++u) {
+                        tsum += jv[u];
+                        qsum = fma(jv[u], jv[u], qsum);
                     }
-                    (kk < 8 ? my0 : my1)[kk & 7] = make_double2(ja + jb, fma(jb, jb, ja * ja));   // columns >= A are never read back
+                    (kk < 8 ? my0 : my1)[kk & 7] = make_double2(tsum, qsum);   // columns >= A are never read back
                     {   // two rows of the other half-tile (chunk c-1's angles 8-15 during steps 0-7, this chunk's 0-7 during 8-15)
                         const double* cc = (kk < 8 ? col1 : col0) + (2 * (kk & 7)) * (2 * kHalfPitch);
                         ra += cc[0];
                         rb += cc[2 * kHalfPitch];
                     }
                     if (HS != 0 && (HS > 0 ? (kk % (HS > 0 ? HS : 1) == 0) : (((i0 + kk) & h_mask) == 0)) && i0 + kk < A) {
-                        hist_add(hrow, ja, PLAIN || row_ok[0], h_shift, h_lo_key, h_last);
-                        hist_add(hrow, jb, PLAIN || row_ok[1], h_shift, h_lo_key, h_last);
+#pragma unroll
+                        for (int u = 0; u < kNS; ++u) hist_add(hrow, jv[u], PLAIN || row_ok[u], h_shift, h_lo_key, h_last);
                         hrow += m.n_bins;
                     }
-                    e1a *= r1a; r1a *= b1[0].q;
-                    e2a *= r2a; r2a *= b2[0].q;
-                    e1b *= r1b; r1b *= b1[1].q;
-                    e2b *= r2b; r2b *= b2[1].q;
+#pragma unroll
+                    for (int u = 0; u < kNS; ++u) {
+                        e1[u] *= r1[u]; r1[u] *= b1[u].q;
+                        e2[u] *= r2[u]; r2[u] *= b2[u].q;
+                    }
                     if (kk == 7) {          // half-tile 1 of the previous chunk is reduced (garbage at c == 0: dropped); half-tile 0 is complete
                         finish_half(i0 - 8, c > 0);
                         __syncwarp();
@@ -362,8 +390,11 @@ __global__ void __launch_bounds__(RESTART ? kWarpsLongM * 32 : kThreadsM, 1) mom
                         __syncwarp();
                     }
                 }
-                sweep_beam_next(b1[0]); sweep_beam_next(b2[0]);
-                sweep_beam_next(b1[1]); sweep_beam_next(b2[1]);
+#pragma unroll
+                for (int u = 0; u < kNS; ++u) {
+                    sweep_beam_next(b1[u]);
+                    sweep_beam_next(b2[u]);
+                }
             }
             // the last chunk's upper half has no sweep to hide behind
 #pragma unroll
@@ -382,22 +413,25 @@ __global__ void __launch_bounds__(RESTART ? kWarpsLongM * 32 : kThreadsM, 1) mom
         // The branch-free division and arccos are evaluated unconditionally, in one basic block with the draw of the next
         // batch's Philox words; the libdevice forms replace them in the rare warps that need IEEE special cases.
         if (SAMPLED) draw_words(w0 + (long long)gridDim.x * batch);
-        double cd[2], dv[2];
+        double cd[kNS], dv[kNS];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kNS; ++u) {
             cd[u] = fm_div(num[u], den[u]);
             dv[u] = fm_acos(cd[u]);
         }
-        if (!(fast && __all_sync(0xffffffffu, fm_mid(den[0]) && fm_mid0(num[0]) && fm_mid(den[1]) && fm_mid0(num[1])))) {
+        bool sums_mid = true;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kNS; ++u) sums_mid = sums_mid && fm_mid(den[u]) && fm_mid0(num[u]);
+        if (!(fast && __all_sync(0xffffffffu, sums_mid))) {
+#pragma unroll
+            for (int u = 0; u < kNS; ++u) {
                 cd[u] = num[u] / den[u];
                 if (cd[u] == CUDART_INF) cd[u] = CUDART_NAN;  // plume.py:125
                 dv[u] = acos(cd[u]);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kNS; ++u) {
             if (active[u]) {
                 c_samples += 1;
                 if (invalid[u]) c_invalid += 1;
