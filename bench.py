@@ -51,8 +51,8 @@ UNIT = 'evals/s'
 WORKLOAD = 'SPT-100 plume+cathode MC, 1e6 samples x 200 angles per GPU, fp64, r=1 m, j_ion materialised'
 ALG_BYTES_PER_EVAL = 8.0 + 144.0 / N_ANGLES
 K2_FP64_PER_EVAL = 10.0    # the reduce-only ALGORITHM per evaluation: 8 recurrence sweep incl. the two Simpson sums + sum + sum of squares
-K2_FP64_EXECUTED = 8.8     # what the kernel executes per evaluation in its sweep since the Simpson sums come from a per-grid table
-                           # (281 fp64 instructions per 16-angle chunk of a sample pair, ncu source page, profiles/r02_k2_ncu_summary.txt)
+K2_FP64_EXECUTED = 8.6     # what the kernel executes per evaluation in its sweep since the Simpson sums come from a per-grid table
+                           # (412 fp64 instructions per 16-angle chunk of a sample triple, ncu source page, profiles/r02_k2_ncu_summary.txt)
 MC_SEED = 20240307
 
 
@@ -279,7 +279,7 @@ def bench_mc(name, n_total, n_angles, scaling, rank, world, dev, local_rank, bar
                                       'stays comparable) / measured DFMA issue peak',
                          'executed_sweep_instr_per_eval': K2_FP64_EXECUTED,
                          'frac_executed_sweep': None if not fp64_peak else K2_FP64_EXECUTED * value / world / fp64_peak,
-                         'executed_note': 'the kernel now takes the Simpson sums from a per-grid table and executes 8.8 fp64 '
+                         'executed_note': 'the kernel now takes the Simpson sums from a per-grid table and executes 8.6 fp64 '
                                           'instructions per evaluation in its sweep (+ ~2.2 at 256 / ~1.2 at 512 angles for the '
                                           'per-sample part); ncu sm__pipe_fp64_cycles_active of the same kernel: '
                                           'profiles/r02_k2_ncu_summary.txt'},

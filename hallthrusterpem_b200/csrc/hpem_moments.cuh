@@ -4,19 +4,19 @@
 // tests/test_plume.py:50-52, scripts/gen_data.py:402-404) for sample counts whose j_ion cannot be stored (BASELINE
 // configs 4-5: 1e8-1e9 samples x up to 512 angles).
 //
-// Mapping.  One persistent block per SM; every THREAD owns TWO samples (s, s + 32) and runs their recurrence sweeps
-// (same arithmetic as K1u) interleaved: eight independent multiply chains per thread, and the per-sample prologue of both
-// samples is one branch-free block (hpem_fastmath.cuh).  The Philox words of a batch are drawn one iteration ahead, beside
-// the latency-bound tail of the previous batch.  The two Simpson sums of plume.py:121-122 come from the grid's table
-// (hpem_qtable.cuh): one lookup per beam instead of two fused multiply-adds per (sample, angle).  The per-angle sums over
-// samples need a transposition (thread = sample for the sweep, thread = angle for the column sums).  The two samples of a
-// thread are combined in registers first,
-//        t = jA + jB,   q = jA^2 + jB^2,
-// so the tile that goes through shared memory holds one (t, q) pair per TWO evaluations: 16-byte conflict-free
-// stores, half the shared-memory traffic of a value-per-evaluation tile (the first version was as busy on the
-// shared-memory pipe as on the fp64 pipe).  Column sums: 2 lanes per column of 16 rows, added into per-warp accumulators;
-// one partial vector per block at the end, merged in block order by moments_finalize_kernel (bit-reproducible for a
-// fixed launch geometry).
+// Mapping.  One persistent block per SM; every THREAD owns NS = 2 or 3 samples (s, s + 32, s + 64) and runs their recurrence
+// sweeps (same arithmetic as K1u) interleaved: four independent multiply chains per sample, and the per-sample prologue
+// of all its samples is one branch-free block (hpem_fastmath.cuh).  The Philox words of a batch are drawn one iteration
+// ahead, beside the latency-bound tail of the previous batch.  The two Simpson sums of plume.py:121-122 come from the
+// grid's table (hpem_qtable.cuh): one lookup per beam instead of two fused multiply-adds per (sample, angle).  The
+// per-angle sums over samples need a transposition (thread = sample for the sweep, thread = angle for the column sums).
+// The samples of a thread are combined in registers first,
+//        t = sum_u j_u,   q = sum_u j_u^2,
+// so the tile that goes through shared memory holds one (t, q) pair per NS evaluations: 16-byte conflict-free
+// stores, half (a third) of the shared-memory traffic of a value-per-evaluation tile (the first version was as busy on
+// the shared-memory pipe as on the fp64 pipe).  Column sums: 2 lanes per column of 16 rows, added into per-warp
+// accumulators; one partial vector per block at the end, merged in block order by moments_finalize_kernel
+// (bit-reproducible for a fixed launch geometry).
 //
 // Histograms: log-linear bins straight from the leading bits of the fp64 pattern (no log), one fire-and-forget reduction
 // per lane to the block's private histogram in global memory (L2 atomics; blocks never share a line) -- see hist_add.
@@ -102,15 +102,11 @@ __device__ __forceinline__ void hist_add(unsigned* hrow, double j, bool ok, int 
 
 // HS: histogram angle stride known at compile time (8, the default), 0 = no histograms, -1 = any power-of-two stride.
 // RESTART: the row is longer than kRestartChunks chunks, the recurrences are re-anchored with exact exps (A > 256).
-// Launch geometry.  Rows of up to 256 angles: 12 warps per SM at 168 registers.  Longer rows (RESTART) run 8 warps at 250
-// registers: the restart block's twelve exponentials no longer spill into the sweep, and the smaller shared-memory
-// footprint leaves the L1 to the quadrature table (B200, 4e7 samples, histograms: 272 angles 9.5 -> 9.8e11 evals/s,
-// 512: 1.12 -> 1.20e12, 640: 1.10 -> 1.23e12; at 256 angles and below 12 warps stay 3-10 % ahead).  Registers come in
-// blocks of four warps, so 9-11 warps cannot have more than 168 either.
+// Launch geometry.  Registers come in blocks of four warps: 12 warps x 168 registers or 8 warps x 255.
 //
 // NS = samples per thread.  Three samples on 8 warps x 255 registers keep as many samples in flight as two on 12 warps, with
 // a third fewer shared-memory stores, column-reduce additions and loop instructions per evaluation: ahead from ~200 angles
-// (4e7 samples, histograms: 224 angles +2 %, 256 +3 %, 512 +6 % over two samples on 8 warps), behind below (128: -2.5 %, 91:
+// (4e7 samples, histograms: 224 angles +2 %, 256 +3 %, 512 +13 % over two samples on 12 warps), behind below (128: -2.5 %, 91:
 // -4 %: the per-sample part dominates there and wants the twelve warps).  Four samples spill (972 vs 1036e9 at 256 angles).
 constexpr int kWarpsLongM = 8;
 constexpr int kLongChunksM = 13;     // rows of >= 13 chunks (> 192 angles) take the three-sample geometry (when instantiated)
