@@ -198,7 +198,10 @@ int hpem_moments_merge(int device, const hpem_moments_layout *layout, int n_part
 
 /* ---- on-device sampler for the input priors (the step before the path: amisc `sample_inputs`, gen_data.py:238) ----
  * Counter-based (Philox4x32-10): the inputs of global sample index i depend only on (seed, i), never on the shard,
- * chunk or GPU that draws them. */
+ * chunk or GPU that draws them.  Stream: call t = 0..4 of sample i has counter (i lo, i hi, t, 0) and key (seed lo, seed hi)
+ * and serves inputs 3t, 3t+1, 3t+2 (enum hpem_input order); uniform j of a call is k 2^-42 with the 42-bit integer
+ * k = (bits 10j..10j+9 of output word 3) << 32 | output word j; Uniform: fma(u, b - a, a), LogUniform:
+ * exp(fma(u, ln b - ln a, ln a)), Normal: Box-Muller with a second stream.  NumPy statement: oracle/sampler_oracle.py. */
 #define HPEM_PRIOR_CONST 0      /* value a */
 #define HPEM_PRIOR_UNIFORM 1    /* U(a, b)            yml: U(a,b), Uniform(a,b), Relative(p) around a nominal */
 #define HPEM_PRIOR_LOGUNIFORM 2 /* LogUniform(a, b)   yml:253,261 */
