@@ -477,6 +477,16 @@ def test_wide_range_fuzz_against_oracle(n_angles, seed, cuda_device):
             out[key] = np.where(sub, np.nan, out[key])
             gmode[key] = np.where(sub, np.nan, gold[key])
         _compare(out, gmode, b, torr, np.array([1.0]), f'fuzz a{n_angles} {mode}')
+    # no j_ion wanted: the two Simpson sums come from the grid's quadrature table (64 angles and more) -- the same lookup the
+    # reduce-only kernel uses -- here with x = (h / alpha)^2 from ~1e-9 (alpha2 ~ 100 rad) to ~1e4 (needle beams)
+    from tests.parity import check_div_angle, check_rel
+    out = plume_cathode(b, 1.0, n_angles=n_angles, torr_2_pa=torr, extras=True, want_j_ion=False)
+    assert 'j_ion' not in out and np.array_equal(out['invalid'].astype(bool), gold['invalid'])
+    cd, cd_ref = np.where(sub, np.nan, out['cos_div']), np.where(sub, np.nan, gold['cos_div'])
+    check_rel(cd, cd_ref, f'fuzz a{n_angles} table cos_div')
+    check_rel(np.where(sub, np.nan, out['T_c']), np.where(sub, np.nan, gold['T_c']), f'fuzz a{n_angles} table T_c')
+    check_div_angle(np.where(sub, np.nan, out['div_angle']), np.where(sub, np.nan, gold['div_angle']), cd, cd_ref,
+                    f'fuzz a{n_angles} table div_angle')
 
 
 @pytest.mark.parametrize('n,n_angles,radii', [(1001, 91, None), (4099, 93, None), (777, 66, None), (1000, 200, None),
