@@ -1514,11 +1514,11 @@ __global__ void __launch_bounds__(kThreadsL) loglike_kernel(const EvalParams p, 
             const double ja = win[mp.lo - i0 + 1], jb = win[mp.lo - i0 + 2];
             const double yh = fma(mp.w, jb - ja, ja);       // linear interpolation on [alpha[lo], alpha[lo+1]]
             const double r = (mp.y - yh) * mp.inv_sigma;
-            ll = fma(-0.5 * r, r, ll);
+            ll = fma(r, r, ll);                             // sum of squared residuals; the factor -1/2 (exact) is applied once below
             if (pred) pred[mp.orig] = yh;
         }
     }
-    if (lp.loglike) lp.loglike[s] = ll;
+    if (lp.loglike) lp.loglike[s] = -0.5 * ll;
 }
 
 // log-sum-exp over the trailing axis (the M Monte-Carlo draws of the nuisance parameters behind one calibration vector):
