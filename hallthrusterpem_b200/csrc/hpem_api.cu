@@ -1095,7 +1095,7 @@ int hpem_measurements_create(const hpem_grid* g, int m, const double* theta, con
         pts[q].y = y[q];
         pts[q].inv_sigma = 1.0 / sigma[q];
         pts[q].orig = q;
-        pts[q].lo = hi - 1;
+        pts[q].rel = hi & (hpem::kChunk - 1);   // (lo + 1) mod 16
     }
     std::vector<int> order(m);
     for (int q = 0; q < m; ++q) order[q] = q;

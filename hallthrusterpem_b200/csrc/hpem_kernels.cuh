@@ -1418,12 +1418,12 @@ __global__ void __launch_bounds__(kThreadsD) eval_direct_kernel(const EvalParams
 // plume.py:142-149), then sum -0.5 ((y - y_hat)/sigma)^2 (scripts/pem_v0/mcmc.py:103).  One thread per sample runs the
 // recurrence sweep once; the measurement points are pre-sorted by |angle| on the host so that the points falling in
 // grid interval [i-1, i] are a contiguous range that is consumed when the sweep reaches angle i.
-struct MeasPoint {       // one probe location, sorted by |theta|
-    double w;            // (|theta| - alpha[lo]) / (alpha[lo+1] - alpha[lo])
+struct __align__(16) MeasPoint {   // one probe location, sorted by |theta|; 32 bytes = two broadcast 16-byte loads
+    double w;            // (|theta| - alpha[lo]) / (alpha[lo+1] - alpha[lo]), [alpha[lo], alpha[lo+1]] = the grid interval that holds |theta|
     double y;            // measured j_ion
     double inv_sigma;    // 1 / standard deviation
     int orig;            // index in the caller's arrays
-    int lo;              // grid interval [alpha[lo], alpha[lo+1]] that holds |theta|
+    int rel;             // (lo + 1) mod 16: position of alpha[lo] in the 17-angle window of the chunk that consumes the point
 };
 struct LoglikeParams {
     int m;                    // number of measurement points
@@ -1509,13 +1509,24 @@ __global__ void __launch_bounds__(kThreadsL) loglike_kernel(const EvalParams p, 
         // intervals [lo, lo+1] with both ends in the window: lo = max(i0 - 1, 0) .. min(i0 + 15, A - 1) - 1
         const int lo_first = max(i0 - 1, 0), hi_last = min(i0 + kChunk - 1, A - 1);
         const int q0 = seg[lo_first], q1 = seg[hi_last];   // warp-uniform range of the sorted points
-        for (int q = q0; q < q1; ++q) {
-            const MeasPoint mp = msm[q];                    // broadcast loads
-            const double ja = win[mp.lo - i0 + 1], jb = win[mp.lo - i0 + 2];
-            const double yh = fma(mp.w, jb - ja, ja);       // linear interpolation on [alpha[lo], alpha[lo+1]]
-            const double r = (mp.y - yh) * mp.inv_sigma;
-            ll = fma(r, r, ll);                             // sum of squared residuals; the factor -1/2 (exact) is applied once below
-            if (pred) pred[mp.orig] = yh;
+        if (pred) {
+            for (int q = q0; q < q1; ++q) {
+                const MeasPoint mp = msm[q];                    // broadcast loads
+                const double ja = win[mp.rel], jb = win[mp.rel + 1];
+                const double yh = fma(mp.w, jb - ja, ja);       // linear interpolation on [alpha[lo], alpha[lo+1]]
+                const double r = (mp.y - yh) * mp.inv_sigma;
+                ll = fma(r, r, ll);                             // sum of squared residuals; the factor -1/2 (exact) is applied once below
+                pred[mp.orig] = yh;
+            }
+        } else {
+#pragma unroll 4
+            for (int q = q0; q < q1; ++q) {
+                const MeasPoint mp = msm[q];
+                const double ja = win[mp.rel], jb = win[mp.rel + 1];
+                const double yh = fma(mp.w, jb - ja, ja);
+                const double r = (mp.y - yh) * mp.inv_sigma;
+                ll = fma(r, r, ll);
+            }
         }
     }
     if (lp.loglike) lp.loglike[s] = -0.5 * ll;
