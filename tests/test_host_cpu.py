@@ -202,6 +202,12 @@ def test_quadrature_table_matches_long_double_sums(n_angles):
     e = np.exp(-x.astype(np.longdouble)[:, None] * i2[None, :])
     rd, rn = (e * wd.astype(np.longdouble)).sum(axis=1), (e * wn.astype(np.longdouble)).sum(axis=1)
     assert np.all(np.abs(nd - rd) <= 5e-16 * np.abs(rd)) and np.all(np.abs(nn - rn) <= 5e-16 * np.abs(rn))
+    # misuse is reported through the status code + hpem_last_error, like every other entry point
+    lib.hpem_last_error.restype = ctypes.c_char_p
+    assert lib.hpem_quadrature_table_eval(1, wd.ctypes.data_as(dptr), wn.ctypes.data_as(dptr), 0, None, None, None) != 0
+    assert b'n_angles' in lib.hpem_last_error()
+    assert lib.hpem_quadrature_table_eval(n_angles, None, wn.ctypes.data_as(dptr), 0, None, None, None) != 0
+    assert lib.hpem_quadrature_table_eval(n_angles, wd.ctypes.data_as(dptr), wn.ctypes.data_as(dptr), 0, None, None, None) == 0
 
 
 def _gloo_worker(rank, world, port, n, n_angles, q):
